@@ -1,0 +1,330 @@
+// attention.cuh — paged attention for decode (q_len = 1), verify (q_len = K+1) and
+// prefill chunks (q_len <= 64) over the 256-token-page KV cache.
+// Replaces sgl_kernel.flash_attn.flash_attn_with_kvcache at layers/attention.py:107-111,128-131:
+//   softmax(q k^T * hd^-1/2 + causal) v, GQA (query head h -> kv head h / (H/KV)),
+//   causal mask aligned to the END of the cache (query j of a sequence sees kv positions
+//   <= context_len - q_len + j), K/V read back from the paged cache (attention.py:82-83).
+//
+// Work decomposition (the problem is tiny and latency-bound at b=1, so the aim is to
+// spread a few hundred KB of KV over as many SMs as possible):
+//   grid = (kv_heads, n_split, batch * n_qtiles), 128 threads.
+//   A CTA owns one kv head, up to TQ query tokens x G=H/KV query heads (R = G*tq <= 64 rows,
+//   padded to MT 16-row MMA tiles) and a contiguous range of 64-token KV chunks.
+//   K/V chunks are staged in shared memory with 16-byte cp.async (coalesced 256 B rows of a
+//   page), double buffered; QK^T and PV run on mma.sync m16n8k16 (bf16, fp32 accumulate)
+//   with ldmatrix fragments; softmax is online in fp32 (exp2 domain).
+//   Warps split (m-tile, token-slice); their partial (m, l, O) are merged through smem,
+//   split-KV partials through a global fp32 scratch + attn_combine_kernel.
+// The grid is static (CUDA-graph friendly): each CTA derives its chunk range from
+// context_lens[] at run time.
+#pragma once
+#include "common.cuh"
+
+namespace ssdk {
+
+constexpr int kAttThreads = 128;
+constexpr int kAttChunk = 64;
+
+struct AttnParams {
+  const __nv_bfloat16* q;        // [B*Q, H, hd]
+  const __nv_bfloat16* k_cache;  // [slots, KV, hd]
+  const __nv_bfloat16* v_cache;
+  const int32_t* block_tables;   // [B, max_blocks]
+  const int32_t* context_lens;   // [B], includes the Q new tokens
+  __nv_bfloat16* out;            // [B*Q, H*hd]
+  float* part_o;                 // [B*Q*H, n_split, hd]
+  float* part_lse;               // [B*Q*H, n_split]
+  int B, Q, H, KV, block_size, max_blocks, n_split, TQ, n_qtiles;
+  float scale_log2;              // softmax scale * log2(e)
+};
+
+SSDK_DEVINL void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz)
+               : "memory");
+}
+SSDK_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+SSDK_DEVINL void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+SSDK_DEVINL void ldmatrix_x4(uint32_t* r, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+SSDK_DEVINL void ldmatrix_x4_trans(uint32_t* r, const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+SSDK_DEVINL void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+SSDK_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int HD, int MT>
+__global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
+  constexpr int LDS = HD + 8;               // padded smem row (bf16 elements)
+  constexpr int TSL = 4 / MT;               // token slices per chunk
+  constexpr int TW = kAttChunk / TSL;       // tokens per warp per chunk (16 * MT)
+  constexpr int NT = TW / 8;                // 8-token score tiles per warp
+  constexpr int KS = HD / 16;               // k-steps over head_dim
+  constexpr int ND = HD / 8;                // 8-wide output tiles over head_dim
+  constexpr int SEG = HD / 8;               // 16-byte segments per K/V row
+
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);            // [2][64][LDS]
+  __nv_bfloat16* sV = sK + 2 * kAttChunk * LDS;                              // [2][64][LDS]
+
+  pdl_wait();
+
+  const int kvh = blockIdx.x, split = blockIdx.y;
+  const int b = blockIdx.z / p.n_qtiles, qt = blockIdx.z % p.n_qtiles;
+  const int G = p.H / p.KV;
+  const int tq = min(p.TQ, p.Q - qt * p.TQ);
+  const int R = G * tq;
+  const int ctx = p.context_lens[b];
+  const int ctx0 = ctx - p.Q;                         // tokens before this forward
+  const int kv_max = ctx0 + qt * p.TQ + tq;           // exclusive upper bound of visible kv for this q-tile
+  const int nch_total = (kv_max + kAttChunk - 1) / kAttChunk;
+  const int cps = (nch_total + p.n_split - 1) / p.n_split;
+  const int ch_begin = split * cps;
+  const int ch_end = min(nch_total, ch_begin + cps);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int mtile = warp % MT, tslice = warp / MT;
+  const int32_t* bt = p.block_tables + (size_t)b * p.max_blocks;
+
+  // ---- Q fragments (registers, whole kernel) ----
+  uint32_t qa[KS][4];
+  {
+    const int r0 = mtile * 16 + g, r1 = r0 + 8;
+    const __nv_bfloat16* q0 = nullptr;
+    const __nv_bfloat16* q1 = nullptr;
+    if (r0 < R) q0 = p.q + ((size_t)(b * p.Q + qt * p.TQ + r0 / G) * p.H + kvh * G + r0 % G) * HD;
+    if (r1 < R) q1 = p.q + ((size_t)(b * p.Q + qt * p.TQ + r1 / G) * p.H + kvh * G + r1 % G) * HD;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk) {
+      const int c = kk * 16 + 2 * t;
+      qa[kk][0] = q0 ? *reinterpret_cast<const uint32_t*>(q0 + c) : 0u;
+      qa[kk][1] = q1 ? *reinterpret_cast<const uint32_t*>(q1 + c) : 0u;
+      qa[kk][2] = q0 ? *reinterpret_cast<const uint32_t*>(q0 + c + 8) : 0u;
+      qa[kk][3] = q1 ? *reinterpret_cast<const uint32_t*>(q1 + c + 8) : 0u;
+    }
+  }
+  // causal limits (exclusive) of this thread's two rows
+  int lim[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = mtile * 16 + g + 8 * h;
+    lim[h] = (r < R) ? (ctx0 + qt * p.TQ + r / G + 1) : 0;
+  }
+
+  float o[ND][4];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+
+  auto load_chunk = [&](int ch, int stage) {
+    const int base = ch * kAttChunk;
+    __nv_bfloat16* dk = sK + stage * kAttChunk * LDS;
+    __nv_bfloat16* dv = sV + stage * kAttChunk * LDS;
+    for (int idx = threadIdx.x; idx < kAttChunk * SEG; idx += kAttThreads) {
+      const int tok = idx / SEG, seg = idx - tok * SEG;
+      const int pos = base + tok;
+      bool valid = pos < kv_max;
+      size_t off = 0;
+      if (valid) {
+        const int blk = bt[pos / p.block_size];
+        valid = blk >= 0;
+        off = (((size_t)blk * p.block_size + pos % p.block_size) * p.KV + kvh) * HD + seg * 8;
+      }
+      cp_async16(dk + tok * LDS + seg * 8, p.k_cache + off, valid);
+      cp_async16(dv + tok * LDS + seg * 8, p.v_cache + off, valid);
+    }
+  };
+
+  if (ch_begin < ch_end) {
+    load_chunk(ch_begin, 0);
+    cp_async_commit();
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      const int stage = (ch - ch_begin) & 1;
+      if (ch + 1 < ch_end) load_chunk(ch + 1, stage ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+
+      const __nv_bfloat16* cK = sK + stage * kAttChunk * LDS;
+      const __nv_bfloat16* cV = sV + stage * kAttChunk * LDS;
+      const int tok0 = tslice * TW;
+
+      // ---- S = Q K^T ----
+      float s[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int kk = 0; kk < KS; kk += 2) {
+          uint32_t kb[4];
+          const int mi = lane >> 3, rr = lane & 7;
+          const __nv_bfloat16* addr = cK + (tok0 + nt * 8 + rr) * LDS + kk * 16 + (mi & 1) * 8 + (mi >> 1) * 16;
+          ldmatrix_x4(kb, addr);
+          mma_bf16_16816(s[nt], qa[kk], kb[0], kb[1]);
+          mma_bf16_16816(s[nt], qa[kk + 1], kb[2], kb[3]);
+        }
+      }
+      // ---- scale, causal mask, online softmax ----
+      const int pos_base = ch * kAttChunk + tok0 + 2 * t;
+      float mnew[2] = {mrow[0], mrow[1]};
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int h = e >> 1;
+          const int pos = pos_base + nt * 8 + (e & 1);
+          const float v = (pos < lim[h]) ? s[nt][e] * p.scale_log2 : -INFINITY;
+          s[nt][e] = v;
+          mnew[h] = fmaxf(mnew[h], v);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mnew[h] = fmaxf(mnew[h], __shfl_xor_sync(0xffffffffu, mnew[h], 1));
+        mnew[h] = fmaxf(mnew[h], __shfl_xor_sync(0xffffffffu, mnew[h], 2));
+      }
+      float corr[2], msafe[2], psum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        msafe[h] = (mnew[h] == -INFINITY) ? 0.f : mnew[h];
+        corr[h] = exp2f(mrow[h] - msafe[h]);  // mrow = -inf -> 0
+        mrow[h] = mnew[h];
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int h = e >> 1;
+          const float pv = exp2f(s[nt][e] - msafe[h]);
+          s[nt][e] = pv;
+          psum[h] += pv;
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) lrow[h] = lrow[h] * corr[h] + psum[h];
+#pragma unroll
+      for (int i = 0; i < ND; ++i) {
+        o[i][0] *= corr[0];
+        o[i][1] *= corr[0];
+        o[i][2] *= corr[1];
+        o[i][3] *= corr[1];
+      }
+      // ---- O += P V ----
+#pragma unroll
+      for (int kk = 0; kk < TW / 16; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int nd = 0; nd < ND; nd += 2) {
+          uint32_t vb[4];
+          const int mi = lane >> 3, rr = lane & 7;
+          const __nv_bfloat16* addr = cV + (tok0 + kk * 16 + (mi & 1) * 8 + rr) * LDS + nd * 8 + (mi >> 1) * 8;
+          ldmatrix_x4_trans(vb, addr);
+          mma_bf16_16816(o[nd], pa, vb[0], vb[1]);
+          mma_bf16_16816(o[nd + 1], pa, vb[2], vb[3]);
+        }
+      }
+      __syncthreads();  // everyone done with this stage before it is refilled
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // ---- finish row sums across the quad, merge token slices through smem ----
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    lrow[h] += __shfl_xor_sync(0xffffffffu, lrow[h], 1);
+    lrow[h] += __shfl_xor_sync(0xffffffffu, lrow[h], 2);
+  }
+  constexpr int LDO = HD + 2;
+  float* sO = reinterpret_cast<float*>(att_smem);  // [4 warps][16 rows][LDO]: O | m | l   (fits: 4*16*130*4 = 33 KB)
+  {
+    float* w = sO + warp * 16 * LDO;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      w[g * LDO + i * 8 + 2 * t] = o[i][0];
+      w[g * LDO + i * 8 + 2 * t + 1] = o[i][1];
+      w[(g + 8) * LDO + i * 8 + 2 * t] = o[i][2];
+      w[(g + 8) * LDO + i * 8 + 2 * t + 1] = o[i][3];
+    }
+    if (t == 0) {
+      w[g * LDO + HD] = mrow[0];
+      w[g * LDO + HD + 1] = lrow[0];
+      w[(g + 8) * LDO + HD] = mrow[1];
+      w[(g + 8) * LDO + HD + 1] = lrow[1];
+    }
+  }
+  __syncthreads();
+  // one (row, column) pair per loop iteration: rows 0..R-1, columns 0..HD-1
+  for (int idx = threadIdx.x; idx < R * HD; idx += kAttThreads) {
+    const int r = idx / HD, d = idx - r * HD;
+    const int mt = r >> 4, rr = r & 15;
+    float mmax = -INFINITY;
+#pragma unroll
+    for (int sl = 0; sl < TSL; ++sl) mmax = fmaxf(mmax, sO[((sl * MT + mt) * 16 + rr) * LDO + HD]);
+    float acc = 0.f, l = 0.f;
+    if (mmax != -INFINITY) {
+#pragma unroll
+      for (int sl = 0; sl < TSL; ++sl) {
+        const float* w = sO + ((sl * MT + mt) * 16 + rr) * LDO;
+        const float wgt = exp2f(w[HD] - mmax);
+        acc += w[d] * wgt;
+        l += w[HD + 1] * wgt;
+      }
+    }
+    const int row_q = b * p.Q + qt * p.TQ + r / G;
+    const int head = kvh * G + r % G;
+    const float val = (l > 0.f) ? acc / l : 0.f;
+    if (p.n_split == 1) {
+      p.out[((size_t)row_q * p.H + head) * HD + d] = f2bf(val);
+    } else {
+      const size_t pr = ((size_t)row_q * p.H + head) * p.n_split + split;
+      p.part_o[pr * HD + d] = val;
+      if (d == 0) p.part_lse[pr] = (l > 0.f) ? mmax + log2f(l) : -INFINITY;
+    }
+  }
+}
+
+// merge split-KV partials: out = sum_s 2^(lse_s - max) o_s / sum_s 2^(lse_s - max)
+__global__ void attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
+                                    __nv_bfloat16* __restrict__ out, int n_split, int hd) {
+  pdl_wait();
+  const size_t row = blockIdx.x;  // (token, head)
+  float mx = -INFINITY;
+  for (int s = 0; s < n_split; ++s) mx = fmaxf(mx, __ldcg(part_lse + row * n_split + s));
+  for (int d = threadIdx.x; d < hd; d += blockDim.x) {
+    float acc = 0.f, wsum = 0.f;
+    if (mx != -INFINITY) {
+      for (int s = 0; s < n_split; ++s) {
+        const float w = exp2f(__ldcg(part_lse + row * n_split + s) - mx);
+        acc += w * __ldcg(part_o + (row * n_split + s) * hd + d);
+        wsum += w;
+      }
+    }
+    out[row * hd + d] = f2bf(wsum > 0.f ? acc / wsum : 0.f);
+  }
+}
+
+}  // namespace ssdk

@@ -1,0 +1,241 @@
+// elementwise.cuh — the HBM/launch-bound glue between GEMMs: embedding + RMSNorm(+residual),
+// per-head norm + RoPE + KV-cache scatter, SiLU*mul, and the per-forward index prep.
+// Every kernel also folds in the fixed-order reduction of the producer GEMM's split-K
+// partials (fp32 [S, M, N]) and the bf16 rounding the reference applies to every
+// F.linear output (SURVEY §8a checklist 1).
+#pragma once
+#include "common.cuh"
+
+namespace ssdk {
+
+// A GEMM result as seen by its consumer: either a plain bf16 matrix [M, ld] or
+// S split-K partials fp32 [S, M, N] to be summed (s = 0..S-1 in order) and rounded to bf16.
+struct GemmOut {
+  const __nv_bfloat16* dense;  // used when S == 0
+  const float* partial;        // used when S >= 1
+  int S;
+  int M;   // rows in the partial buffer
+  int N;   // row width of the partial buffer / dense ld
+};
+
+SSDK_DEVINL float gemm_out_at(const GemmOut& g, int m, int n) {
+  if (g.S == 0) return bf2f(g.dense[(size_t)m * g.N + n]);
+  float acc = 0.f;
+  for (int s = 0; s < g.S; ++s) acc += __ldcg(g.partial + ((size_t)s * g.M + m) * g.N + n);
+  return bf16_round(acc);
+}
+// 8 consecutive columns starting at n (n % 8 == 0)
+SSDK_DEVINL void gemm_out_at8(const GemmOut& g, int m, int n, float* f) {
+  if (g.S == 0) {
+    uint4 v = *reinterpret_cast<const uint4*>(g.dense + (size_t)m * g.N + n);
+    unpack_bf16x8(v, f);
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = 0.f;
+  for (int s = 0; s < g.S; ++s) {
+    const float4* p = reinterpret_cast<const float4*>(g.partial + ((size_t)s * g.M + m) * g.N + n);
+    float4 a = __ldcg(p), b = __ldcg(p + 1);
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+    f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = bf16_round(f[i]);
+}
+
+// ----------------------------------------------------------------------------------
+// prep: positions / slot_mapping / context_lens for one forward of `batch` sequences
+// with q_len tokens each, token j of sequence b at position ctx0[b] + pos_offset + j.
+// Mirrors prepare_decode_tensors_from_seqs (helpers/runner_helpers.py:50-108) on device.
+// ----------------------------------------------------------------------------------
+__global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __restrict__ block_tables,
+                            int max_blocks, int block_size, int batch, int q_len, int pos_offset,
+                            int64_t* __restrict__ positions, int32_t* __restrict__ slot_mapping,
+                            int32_t* __restrict__ context_lens) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch * q_len) {
+    const int b = i / q_len, j = i - b * q_len;
+    const int pos = ctx0[b] + pos_offset + j;
+    positions[i] = pos;
+    const int blk = block_tables[(size_t)b * max_blocks + pos / block_size];
+    slot_mapping[i] = (blk < 0) ? -1 : blk * block_size + pos % block_size;
+  }
+  if (i < batch) context_lens[i] = ctx0[i] + pos_offset + q_len;
+}
+
+// ----------------------------------------------------------------------------------
+// (embedding gather |) (split-K reduce |) residual add + RMSNorm.   grid = M rows.
+//   x row      = embed[ids[m*ids_stride] - vocab_start]  (ids != nullptr; rows outside the
+//                local vocab shard contribute zeros — VocabParallelEmbedding, embed_head.py:49-58)
+//              | GEMM output (dense or partials)
+//   r          = x + residual_in            (fp32; residual_in may be null: r = x)
+//   residual_out = bf16(r)
+//   y          = bf16(r * rsqrt(mean(r^2) + eps) * w)        (layers/layernorm.py:64-88, compiled form)
+// ----------------------------------------------------------------------------------
+struct NormParams {
+  GemmOut x;
+  const int64_t* ids;
+  int ids_stride;
+  const __nv_bfloat16* embed;
+  int vocab_start, vocab_rows;
+  const __nv_bfloat16* residual_in;
+  const __nv_bfloat16* w;
+  float eps;
+  __nv_bfloat16* y;
+  __nv_bfloat16* residual_out;
+  int d;
+};
+
+__global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
+  extern __shared__ float rbuf[];  // d floats
+  __shared__ float red[32];
+  pdl_wait();
+  const int m = blockIdx.x;
+  const int d = p.d;
+  const __nv_bfloat16* erow = nullptr;
+  bool zero_row = false;
+  if (p.ids) {
+    const long long id = p.ids[(size_t)m * p.ids_stride] - p.vocab_start;
+    if (id < 0 || id >= p.vocab_rows) zero_row = true;
+    else erow = p.embed + (size_t)id * d;
+  }
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
+    float x[8];
+    if (p.ids) {
+      if (zero_row) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+      } else {
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + i), x);
+      }
+    } else {
+      gemm_out_at8(p.x, m, i, x);
+    }
+    if (p.residual_in) {
+      float r[8];
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual_in + (size_t)m * d + i), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += r[j];
+    }
+    if (p.residual_out) *reinterpret_cast<uint4*>(p.residual_out + (size_t)m * d + i) = pack_bf16x8(x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      rbuf[i + j] = x[j];
+      ss += x[j] * x[j];
+    }
+  }
+  ss = block_sum(ss, red);
+  const float rstd = rsqrtf(ss / (float)d + p.eps);
+  if (p.y) {
+    for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
+      float w[8], o[8];
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(p.w + i), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rbuf[i + j] * rstd * w[j];
+      *reinterpret_cast<uint4*>(p.y + (size_t)m * d + i) = pack_bf16x8(o);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// (split-K reduce |) [per-head RMSNorm |] NeoX RoPE on q,k + KV-cache scatter.
+// grid = (M, ceil((H+2KV)/4)), block = 128: one warp per head.
+//   q,k: optional RMSHeadNorm (qwen3.py:97-103; layernorm.py:16-27 compiled form:
+//        bf16(x * rsqrt(mean x^2 + eps) * w)), then
+//        y1 = x1*cos - x2*sin, y2 = x2*cos + x1*sin in fp32 -> bf16 (rotary_embedding.py:6-17)
+//   k,v rows go to cache slot slot_mapping[m] (skip -1)  (attention.py:10-41)
+// ----------------------------------------------------------------------------------
+struct RopeParams {
+  GemmOut qkv;
+  const int64_t* positions;
+  const int32_t* slot_mapping;
+  const float* rope_table;  // [max_pos, hd]: cos[0:hd/2] | sin[0:hd/2]
+  const __nv_bfloat16* q_norm_w;
+  const __nv_bfloat16* k_norm_w;
+  float norm_eps;
+  __nv_bfloat16* q_out;    // [M, H*hd]
+  __nv_bfloat16* k_cache;  // [slots, KV*hd]
+  __nv_bfloat16* v_cache;
+  int heads, kv_heads, head_dim;
+};
+
+__global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
+  pdl_wait();
+  const int m = blockIdx.x;
+  const int head = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int H = p.heads, KV = p.kv_heads, hd = p.head_dim, half = hd >> 1;
+  if (head >= H + 2 * KV) return;
+  const int kind = head < H ? 0 : (head < H + KV ? 1 : 2);  // q, k, v
+  const int col0 = head * hd;
+  const int slot = p.slot_mapping[m];
+
+  if (kind == 2) {
+    if (slot < 0) return;
+    __nv_bfloat16* dst = p.v_cache + ((size_t)slot * KV + (head - H - KV)) * hd;
+    for (int i = lane; i < hd; i += 32) dst[i] = f2bf(gemm_out_at(p.qkv, m, col0 + i));
+    return;
+  }
+  if (kind == 1 && slot < 0) return;
+
+  // each lane owns pairs (i, i + half), i = lane, lane+32, ...   (hd <= 256)
+  float x1[4], x2[4];
+  int np = 0;
+  float ss = 0.f;
+  for (int i = lane; i < half; i += 32, ++np) {
+    x1[np] = gemm_out_at(p.qkv, m, col0 + i);
+    x2[np] = gemm_out_at(p.qkv, m, col0 + half + i);
+    ss += x1[np] * x1[np] + x2[np] * x2[np];
+  }
+  const __nv_bfloat16* nw = (kind == 0) ? p.q_norm_w : p.k_norm_w;
+  if (nw) {
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)hd + p.norm_eps);
+    int t = 0;
+    for (int i = lane; i < half; i += 32, ++t) {
+      x1[t] = bf16_round(x1[t] * rstd * bf2f(nw[i]));
+      x2[t] = bf16_round(x2[t] * rstd * bf2f(nw[half + i]));
+    }
+  }
+  const long long pos = p.positions[m];
+  const float* cs = p.rope_table + (size_t)pos * hd;
+  __nv_bfloat16* dst = (kind == 0) ? p.q_out + (size_t)m * H * hd + (size_t)head * hd
+                                   : p.k_cache + ((size_t)slot * KV + (head - H)) * hd;
+  int t = 0;
+  for (int i = lane; i < half; i += 32, ++t) {
+    const float c = cs[i], s = cs[half + i];
+    dst[i] = f2bf(x1[t] * c - x2[t] * s);
+    dst[half + i] = f2bf(x2[t] * c + x1[t] * s);
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// SiLU(gate) * up for the split-K (non-fused-epilogue) gate|up GEMM and the stand-alone op.
+// x: [M, 2*ffn] (dense or partials) -> out bf16 [M, ffn]
+// ----------------------------------------------------------------------------------
+__global__ void silu_mul_kernel(GemmOut x, __nv_bfloat16* __restrict__ out, int M, int ffn) {
+  pdl_wait();
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (idx >= M * ffn) return;
+  const int m = idx / ffn, n = idx - m * ffn;
+  float g[8], u[8], h[8];
+  gemm_out_at8(x, m, n, g);
+  gemm_out_at8(x, m, ffn + n, u);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = (g[j] / (1.0f + __expf(-g[j]))) * u[j];
+  *reinterpret_cast<uint4*>(out + (size_t)m * ffn + n) = pack_bf16x8(h);
+}
+
+// gather `rows` rows (the last token of each sequence) of a [M, d] matrix: out[b] = x[b*q_len + q_len-1]
+__global__ void gather_last_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int batch,
+                                        int q_len, int d) {
+  pdl_wait();
+  const int b = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * q_len + q_len - 1) * d);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b * d);
+  for (int i = threadIdx.x; i < d / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace ssdk

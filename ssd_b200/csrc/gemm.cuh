@@ -1,0 +1,225 @@
+// gemm.cuh — weight-streaming small-M GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   Y[M, N] = X[M, K] · W[N, K]^T        M <= 64 tokens, bf16 in, fp32 accumulate, bf16 out
+//
+// Replaces every F.linear on the decode/verify path of the reference
+// (layers/linear.py:98,196; layers/embed_head.py:95,111).  With M <= 7 the op is a pure
+// HBM stream of W (arithmetic intensity ~M flop/B), so the design goal is bytes in
+// flight, not tensor throughput:
+//   * swap-AB: the 128 weight rows of a tile are the UMMA "M" dimension, the (padded)
+//     tokens are the UMMA "N" dimension (16/32/64), so one tcgen05.mma consumes a
+//     128x16 (x bf16) weight slab whatever M is; the accumulator D[128 x UMMA_N] fp32
+//     lives in TMEM (32/64 columns).
+//   * W and X tiles arrive by TMA (cp.async.bulk.tensor.2d) into 128B-swizzled shared
+//     memory, kStages deep, mbarrier full/empty ring; W is tagged evict-first (read
+//     once per forward), X evict-last (re-read by every CTA from L2).
+//   * warp-specialised: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator +
+//     MMA issuer (one lane), warps 2-5 = epilogue (tcgen05.ld -> registers -> global).
+//   * split-K over blockIdx.y fills the 148 SMs when N/128 is small; partial sums go to
+//     an fp32 [S, M, N] buffer which the *consumer* kernel (norm / rope / silu) reduces
+//     in a fixed order, so results are deterministic.
+//   * epilogues: bf16 store, fp32 split-K partial, or fused SiLU(gate)*up where a tile is
+//     64 gate rows + 64 up rows of the packed gate|up matrix (layers/activation.py:11-14).
+//   * PDL: weight tiles of the first kStages are requested BEFORE griddepcontrol.wait, so
+//     the HBM stream of this GEMM starts under the tail of the previous kernel.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace ssdk {
+
+constexpr int kBlockK = 64;    // bf16 per k-block = 128 B = one swizzle row
+constexpr int kTileRows = 128; // weight rows per CTA = UMMA_M
+constexpr int kGemmThreads = 192;
+
+enum GemmEpi { EPI_BF16 = 0, EPI_PARTIAL = 1, EPI_SILU = 2 };
+
+struct GemmParams {
+  void* out;          // EPI_BF16/EPI_SILU: bf16 [M, ldo]; EPI_PARTIAL: fp32 [S, M, N]
+  int M;              // valid tokens (<= UMMA_N)
+  int N;              // output width (weight rows; for EPI_SILU the ffn width)
+  int ldo;            // output row stride in elements
+  int num_kb;         // total k-blocks (K / 64)
+  int kb_per_split;   // k-blocks per blockIdx.y
+  int tile_rows;      // output columns per tile: 128 (plain) or 64 (silu)
+  int hi_row_offset;  // W row offset of the second 64-row half: 64 (plain) or ffn (silu)
+};
+
+template <int UMMA_N>
+struct GemmCfg {
+  static constexpr int kABytes = kTileRows * kBlockK * 2;  // 16384
+  static constexpr int kBBytes = UMMA_N * kBlockK * 2;     // 2048 / 4096 / 8192
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (UMMA_N == 16) ? 6 : (UMMA_N == 32 ? 5 : 4);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
+  static constexpr int kTmemCols = (UMMA_N <= 32) ? 32 : 64;
+};
+
+template <int UMMA_N, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, GemmParams p) {
+  using Cfg = GemmCfg<UMMA_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  // 128B swizzle needs 1024 B aligned tiles
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int kb0 = blockIdx.y * p.kb_per_split;
+  const int nkb = min(p.kb_per_split, p.num_kb - kb0);
+  const int row_lo = (EPI == EPI_SILU) ? tile * 64 : tile * kTileRows;
+  const int row_hi = row_lo + p.hi_row_offset;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmX);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  // let the next kernel in the stream start its own prologue / weight prefetch
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int pre = min(nkb, kStages);
+      // weights do not depend on the previous kernel: request them before the grid dependency
+      for (int i = 0; i < pre; ++i) {
+        uint8_t* a_s = smem + i * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
+        const int k = (kb0 + i) * kBlockK;
+        tma_load_2d(a_s, &tmW, &full_bar[i], k, row_lo, kEvictFirst);
+        tma_load_2d(a_s + Cfg::kABytes / 2, &tmW, &full_bar[i], k, row_hi, kEvictFirst);
+      }
+      pdl_wait();  // X is produced by the previous kernel
+      for (int i = 0; i < pre; ++i) {
+        uint8_t* b_s = smem + i * Cfg::kStageBytes + Cfg::kABytes;
+        tma_load_2d(b_s, &tmX, &full_bar[i], (kb0 + i) * kBlockK, 0, kEvictLast);
+      }
+      for (int i = pre; i < nkb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* a_s = smem + s * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        const int k = (kb0 + i) * kBlockK;
+        tma_load_2d(a_s, &tmW, &full_bar[s], k, row_lo, kEvictFirst);
+        tma_load_2d(a_s + Cfg::kABytes / 2, &tmW, &full_bar[s], k, row_hi, kEvictFirst);
+        tma_load_2d(a_s + Cfg::kABytes, &tmX, &full_bar[s], k, 0, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_umma_idesc_bf16(kTileRows, UMMA_N);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        uint8_t* a_s = smem + s * Cfg::kStageBytes;
+        const uint64_t adesc = make_umma_desc_k128(a_s);
+        const uint64_t bdesc = make_umma_desc_k128(a_s + Cfg::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in 16 B units
+          umma_bf16_ss(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+      }
+      umma_commit(&tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    pdl_wait();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    uint32_t r[UMMA_N];
+#pragma unroll
+    for (int c = 0; c < UMMA_N / 16; ++c) tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(q * 32) << 16) + c * 16, r + c * 16);
+    tmem_ld_wait();
+
+    if (EPI == EPI_BF16) {
+      const int n = row_lo + row;
+      if (n < p.N) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+        for (int m = 0; m < UMMA_N; ++m)
+          if (m < p.M) out[(size_t)m * p.ldo + n] = f2bf(__uint_as_float(r[m]));
+      }
+    } else if (EPI == EPI_PARTIAL) {
+      const int n = row_lo + row;
+      if (n < p.N) {
+        float* out = reinterpret_cast<float*>(p.out) + (size_t)blockIdx.y * p.M * p.N;
+#pragma unroll
+        for (int m = 0; m < UMMA_N; ++m)
+          if (m < p.M) out[(size_t)m * p.N + n] = __uint_as_float(r[m]);
+      }
+    } else {
+      // SiLU(gate) * up: rows 0..63 = gate, 64..127 = up of the same 64 output columns.
+      // All MMAs have retired (tmem_full), so pipeline stage 0 is free to stage the exchange.
+      float* ex = reinterpret_cast<float*>(smem);
+      constexpr int LD = UMMA_N + 1;
+#pragma unroll
+      for (int m = 0; m < UMMA_N; ++m) ex[row * LD + m] = __uint_as_float(r[m]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;  // 0..127
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+      for (int idx = e; idx < 64 * p.M; idx += 128) {
+        const int j = idx & 63, m = idx >> 6;
+        const int n = row_lo + j;
+        if (n < p.N) {
+          // the reference rounds the gate|up linear output to bf16 before SiluAndMul
+          const float g = bf16_round(ex[j * LD + m]);
+          const float u = bf16_round(ex[(64 + j) * LD + m]);
+          const float h = (g / (1.0f + __expf(-g))) * u;
+          out[(size_t)m * p.ldo + n] = f2bf(h);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, Cfg::kTmemCols);
+}
+
+// y[m, n] = bf16( sum_s P[s, m, n] )  — fixed-order split-K reduction (stand-alone op only;
+// inside the engine the consumer kernels fold this in).
+__global__ void splitk_reduce_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ y, int S, int M, int N,
+                                     int ldy) {
+  pdl_wait();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int m = idx / N, n = idx - m * N;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += P[(size_t)s * M * N + idx];
+  y[(size_t)m * ldy + n] = f2bf(acc);
+}
+
+}  // namespace ssdk
