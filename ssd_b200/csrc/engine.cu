@@ -320,7 +320,8 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
     part = std::max(part, need(2 * m.ffn, m.d));
     part = std::max(part, need(m.d, m.ffn));
   }
-  Workspace& w = e->ws;
+  Workspace scratch_ws;
+  Workspace& w = base ? e->ws : scratch_ws;  // measuring (base == nullptr) must not clobber bound pointers
   const int K = e->rt.spec_k, MB = e->rt.max_batch;
   w.hidden = (bf16*)take((size_t)kMaxTokens * dmax * 2);
   w.residual = (bf16*)take((size_t)kMaxTokens * dmax * 2);

@@ -247,6 +247,15 @@ class PairRunner:
     def logits_last(self, batch: int, which: int = L.TARGET) -> torch.Tensor:
         return _from_ptr(self.lib.ssdk_logits_last(self.h), (batch, self.spec[which].vocab), self.device)
 
+    def step_io_bytes(self) -> tuple[int, int]:
+        """(H2D, D2H) bytes ssdk_spec_step moves per call: the step block and the result block
+        (layout_step() in csrc/engine.cu; every field 16-byte aligned)."""
+        a = lambda n: (n + 15) // 16 * 16
+        MB, mbk, K = self.max_batch, self.max_blocks, self.K
+        h2d = a(MB * 4) + a(MB * 8) + 2 * a(MB * 4) + 16 + 2 * a(MB * mbk * 4)
+        d2h = a(a(MB * (K + 1) * 8) + a(MB * 4) + MB * 8)
+        return h2d, d2h
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ssdk_launch_count(self.h))

@@ -1,0 +1,143 @@
+"""CPU tests of the host-side mirror of the reference's scheduler / block manager / sequence bookkeeping
+(the producers of the hot path's inputs: block tables, ctx lens, recovery tokens)."""
+import random
+import types
+
+import pytest
+
+from ssd_b200.engine.block_manager import BlockManager
+from ssd_b200.engine.scheduler import Scheduler
+from ssd_b200.engine.sequence import Sequence, SequenceStatus
+from ssd_b200.sampling_params import SamplingParams
+
+
+def _cfg(**kw):
+    d = dict(max_num_seqs=2, max_num_batched_tokens=4096, max_model_len=1024, eos=1, speculate=True, speculate_k=4,
+             kvcache_block_size=16, num_kvcache_blocks=64)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+@pytest.fixture(autouse=True)
+def _bs():
+    Sequence.block_size = 16
+    yield
+    Sequence.block_size = 256
+
+
+def test_block_hash_is_xxh64_chain():
+    import numpy as np
+    import xxhash
+    toks = list(range(16))
+    h0 = BlockManager.compute_hash(toks)
+    assert h0 == xxhash.xxh64(np.array(toks).tobytes()).intdigest()
+    h = xxhash.xxh64()
+    h.update(h0.to_bytes(8, "little"))
+    h.update(np.array(toks).tobytes())
+    assert BlockManager.compute_hash(toks, h0) == h.intdigest()
+
+
+def test_allocate_prefix_reuse_and_refcounts():
+    bm = BlockManager(8, 16, max_model_len=1024)
+    a = Sequence(list(range(40)))
+    bm.allocate(a)
+    assert len(a.block_table) == 3 and a.num_cached_tokens == 0
+    b = Sequence(list(range(32)) + [99] * 5)  # shares two full blocks with a
+    bm.allocate(b)
+    assert b.block_table[:2] == a.block_table[:2] and b.block_table[2] != a.block_table[2]
+    assert b.num_cached_tokens == 32
+    assert bm.blocks[a.block_table[0]].refs == 2
+    bm.deallocate(a)
+    assert bm.blocks[b.block_table[0]].refs == 1
+    bm.deallocate(b)
+    assert len(bm.free_block_ids) == 8 and not bm.used_block_ids
+
+
+def test_may_append_reserves_lookahead_and_trim_returns_it():
+    bm = BlockManager(8, 16, max_model_len=1024)
+    s = Sequence(list(range(30)))
+    bm.allocate(s)
+    assert len(s.block_table) == 2
+    assert bm.can_append(s, 5)
+    bm.may_append(s, 5)  # 30 + 5 = 35 tokens -> 3 blocks
+    assert len(s.block_table) == 3
+    bm.trim(s, 2)
+    assert len(s.block_table) == 2 and len(bm.free_block_ids) == 6
+    assert not BlockManager(8, 16, max_model_len=32).can_append(s, 5)
+
+
+def test_spec_postprocess_truncation_rules():
+    sch = Scheduler(_cfg(), draft_cfg=types.SimpleNamespace(num_kvcache_blocks=64))
+    s = Sequence(list(range(10, 20)), SamplingParams(temperature=0.0, max_new_tokens=6, ignore_eos=False))
+    sch.add(s)
+    seqs, is_prefill = sch.schedule()
+    assert is_prefill and seqs == [s] and s.block_table and s.draft_block_table
+    s.recovery_token_id = 7
+    s.num_cached_tokens = s.num_draft_cached_tokens = 10
+    seqs, is_prefill = sch.schedule()
+    assert not is_prefill
+    sch.postprocess_speculate([s], [[7, 8, 9]], [5])
+    assert s.token_ids[-3:] == [7, 8, 9] and s.recovery_token_id == 5 and s.num_cached_tokens == 13
+    # EOS inside the suffix: truncate after it and finish
+    sch.schedule()
+    sch.postprocess_speculate([s], [[5, 1, 4, 4]], [3])
+    assert s.token_ids[-2:] == [5, 1] and s.is_finished and not s.block_table and not sch.running
+
+
+def test_spec_postprocess_max_new_tokens_and_block_sealing():
+    sch = Scheduler(_cfg(), draft_cfg=types.SimpleNamespace(num_kvcache_blocks=64))
+    s = Sequence(list(range(100, 114)), SamplingParams(temperature=0.0, max_new_tokens=7, ignore_eos=True))
+    sch.add(s)
+    sch.schedule()
+    s.recovery_token_id = 2
+    s.num_cached_tokens = s.num_draft_cached_tokens = 14
+    sch.schedule()
+    assert len(s.block_table) == 2  # 14 + K + 1 = 19 tokens -> look-ahead block reserved
+    sch.postprocess_speculate([s], [[2, 3, 4]], [9])  # crosses the 16-token boundary: block 0 is sealed
+    assert sch.block_manager.blocks[s.block_table[0]].digest != -1
+    assert sch.draft_block_manager.blocks[s.draft_block_table[0]].digest != -1
+    sch.schedule()
+    sch.postprocess_speculate([s], [[9, 9, 9, 9, 9]], [0])  # only 4 tokens of room left
+    assert s.num_completion_tokens == 7 and s.is_finished
+
+
+def test_scheduler_random_walk_invariants():
+    """Random accept lengths: block tables always cover ctx + K + 1 slots at step time, nothing leaks."""
+    rng = random.Random(0)
+    sch = Scheduler(_cfg(num_kvcache_blocks=48, max_num_seqs=3), draft_cfg=types.SimpleNamespace(num_kvcache_blocks=48))
+    seqs = [Sequence([rng.randrange(2, 50) for _ in range(rng.randrange(5, 40))],
+                     SamplingParams(temperature=0.0, max_new_tokens=60, ignore_eos=True)) for _ in range(5)]
+    for s in seqs:
+        sch.add(s)
+    steps = 0
+    while not sch.is_finished() and steps < 500:
+        steps += 1
+        batch, is_prefill = sch.schedule()
+        assert batch
+        if is_prefill:
+            for s in batch:
+                s.recovery_token_id = 3
+                s.num_cached_tokens = s.num_draft_cached_tokens = s.num_prompt_tokens
+            continue
+        for s in batch:
+            need = -(-(s.num_tokens + 5) // 16)
+            assert len(s.block_table) >= need and len(s.draft_block_table) >= need
+            assert s.num_cached_tokens == s.num_tokens
+        sch.postprocess_speculate(batch, [[s.recovery_token_id] + [4] * rng.randrange(0, 5) for s in batch], [3] * len(batch))
+    assert sch.is_finished()
+    assert all(s.num_completion_tokens == 60 for s in seqs)
+    for bm in (sch.block_manager, sch.draft_block_manager):
+        assert len(bm.free_block_ids) == 48 and not bm.used_block_ids
+
+
+def test_compat_shim_exposes_reference_names():
+    import ssd_b200.compat as cm
+    cm.install()
+    from ssd import LLM, SamplingParams as SP  # noqa: F401
+    from ssd.engine.llm_engine import METRICS
+    import ssd.paths as P
+    for k in ("cache_hits", "accepted_suffix_lens_with_recovery", "prefill_total_time", "decode_total_time",
+              "prefill_total_tokens", "decode_total_tokens", "target_step_times", "target_verify_times"):
+        assert k in METRICS
+    assert hasattr(P, "DATASET_PATHS") and hasattr(P, "HF_CACHE_DIR") and hasattr(P, "EAGLE3_QWEN_32B")
+    assert SP().temperature == 1.0 and SP().max_new_tokens == 256 and SP().draft_temperature is None

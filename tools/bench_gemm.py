@@ -1,9 +1,12 @@
 """Micro-benchmark of the weight-streaming GEMM at the shapes of the BASELINE models: achieved HBM GB/s
 (weight bytes / CUDA-event time, L2 flushed between launches) next to torch (cuBLAS) on the same shapes."""
 import json
+import os
 import sys
 
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from ssd_b200 import ops
 
