@@ -230,6 +230,7 @@ struct Workspace {
   int64_t* ids_in;      // [kMaxTokens]  (forward_tokens input)
   int64_t* out_tok;     // [max_batch]   (forward_tokens sampled output)
   bf16 *logits_q, *logits_p, *logits_last;
+  bf16 *logits_shard, *logits_gather;  // tensor-parallel lm_head: local [rows, V/tp] and all-gathered [tp, rows, V/tp]
   // device copy of the step parameters (one contiguous block, see StepBlock)
   uint8_t* step_dev;
   int32_t* n_accept;
@@ -348,6 +349,8 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.logits_q = (bf16*)take((size_t)MB * std::max(K, 1) * vmax * 2);
   w.logits_p = (bf16*)take((size_t)MB * (K + 1) * vmax * 2);
   w.logits_last = (bf16*)take((size_t)kMaxTokens * vmax * 2);
+  w.logits_shard = (bf16*)take((size_t)kMaxTokens * vmax * 2);
+  w.logits_gather = (bf16*)take((size_t)kMaxTokens * vmax * 2);
   w.step_dev = take(e->step_bytes);
   w.samp_partial = (ArgMax*)take((size_t)kMaxTokens * kSampleChunks * sizeof(ArgMax));
   w.samp_counters = (unsigned*)take(kMaxTokens * 4);
@@ -469,6 +472,20 @@ static int enqueue_tp_allreduce(ssdk_engine* e, Launcher& L, int S, int M, int N
   return 0;
 }
 
+// [tp, rows, Vs] (all-gather layout) -> [rows, ld] with column r*Vs + v   (torch.cat(parts, -1), embed_head.py:98-99)
+__global__ void unshard_logits_kernel(const bf16* __restrict__ gathered, bf16* __restrict__ out, int tp, int rows, int Vs,
+                                      int64_t ld) {
+  pdl_wait();
+  const int64_t n8 = (int64_t)tp * rows * (Vs / 8);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v8 = (int)(i % (Vs / 8));
+    const int64_t t = i / (Vs / 8);
+    const int m = (int)(t % rows), r = (int)(t / rows);
+    const uint4 val = *reinterpret_cast<const uint4*>(gathered + ((size_t)r * rows + m) * Vs + (size_t)v8 * 8);
+    *reinterpret_cast<uint4*>(out + (size_t)m * ld + (size_t)r * Vs + (size_t)v8 * 8) = val;
+  }
+}
+
 static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
   Model& m = e->model[f.which];
   Workspace& w = e->ws;
@@ -581,8 +598,19 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     } else if (f.logits_mode == 2) {
       rows = f.B;
     }
-    if (tp > 1) return fail("tensor-parallel lm_head gather is not wired in this build");
-    CKI(enqueue_gemm(e, L, x, m.lm_head, rows, EPI_BF16, f.logits_out, (int)f.logits_ld, m.vocab_local, nullptr));
+    if (tp == 1) {
+      CKI(enqueue_gemm(e, L, x, m.lm_head, rows, EPI_BF16, f.logits_out, (int)f.logits_ld, m.vocab_local, nullptr));
+    } else {
+      // ParallelLMHead (embed_head.py:94-116): per-rank vocab shard, gathered and concatenated on rank 0
+      const int Vs = m.vocab_local;
+      if (Vs % 8) return fail("tensor-parallel lm_head: vocab shard %d not a multiple of 8", Vs);
+      CKI(enqueue_gemm(e, L, x, m.lm_head, rows, EPI_BF16, w.logits_shard, Vs, Vs, nullptr));
+      CKN(ncclAllGather(w.logits_shard, w.logits_gather, (size_t)rows * Vs, ncclBfloat16, e->comm, L.st));
+      L.barrier_op();
+      if (m.cfg.tp_rank == 0 && f.logits_out)
+        CKI(L.go(unshard_logits_kernel, dim3(num_sms()), dim3(256), 0, (const bf16*)w.logits_gather, f.logits_out, tp, rows,
+                 Vs, f.logits_ld));
+    }
   }
   return 0;
 }
@@ -657,8 +685,11 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
   const int32_t* btt = (const int32_t*)(w.step_dev + e->off_btt);
   const int32_t* btd = (const int32_t*)(w.step_dev + e->off_btd);
 
-  CKI(L.go(init_tokens_kernel, dim3(1), dim3(64), 0, (const int64_t*)rec_in, w.tok_buf, B, K + 1));
-  for (int k = 0; k <= K; ++k) {
+  const int tp = tgt.cfg.tp_size, tp_rank = tgt.cfg.tp_rank;
+  if (tp > 1 && !e->comm) return fail("tensor parallel spec step without a NCCL communicator");
+  if (tp_rank == 0 && !drf.present) return fail("rank 0 needs the draft model");
+  if (drf.present) CKI(L.go(init_tokens_kernel, dim3(1), dim3(64), 0, (const int64_t*)rec_in, w.tok_buf, B, K + 1));
+  for (int k = 0; k <= K && drf.present; ++k) {
     Fwd f;
     f.which = SSDK_DRAFT; f.B = B; f.Q = 1; f.ids = w.tok_buf + k; f.ids_stride = K + 1;
     f.ctx0 = ctx; f.block_tables = btd; f.pos_offset = k;
@@ -675,6 +706,11 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
       CKI(L.go(sample_kernel, dim3(kSampleChunks, B), dim3(256), 0, sp));
     }
   }
+  if (tp > 1) {
+    // the draft is pinned to rank 0: ship its K tokens (+ recovery) to the other ranks device-side
+    CKN(ncclBroadcast(w.tok_buf, w.tok_buf, (size_t)B * (K + 1), ncclInt64, 0, e->comm, L.st));
+    L.barrier_op();
+  }
   {
     Fwd f;
     f.which = SSDK_TARGET; f.B = B; f.Q = K + 1; f.ids = w.tok_buf; f.ids_stride = 1;
@@ -682,7 +718,7 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
     f.logits_out = w.logits_p; f.logits_ld = V;
     CKI(enqueue_forward(e, L, f));
   }
-  {
+  if (tp_rank == 0) {
     VerifyParams vp;
     vp.lp = w.logits_p; vp.lq = w.logits_q; vp.spec = w.tok_buf; vp.temps_t = tt; vp.temps_q = tq;
     vp.cache_hits = nullptr; vp.jit = e->rt.jit_speculate; vp.B = B; vp.K = K; vp.V = V;
@@ -690,6 +726,12 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
     vp.row_part = w.ver_rows; vp.rec_part = w.ver_rec; vp.counters = w.ver_counters;
     vp.dyn = seed_step; vp.sub = 15;
     CKI(L.go(verify_kernel, dim3(kVerifyCtas), dim3(kVerifyThreads), 0, vp));
+  }
+  if (tp > 1) {
+    // rank 0 holds the verdict: broadcast it so that every rank (SPMD host engines, resident loop) sees the same
+    // tokens / accept counts / recovery tokens
+    CKN(ncclBroadcast(w.out_dev, w.out_dev, e->out_bytes, ncclChar, 0, e->comm, L.st));
+    L.barrier_op();
   }
   if (advance) {
     CKI(L.go(advance_kernel, dim3(1), dim3(64), 0, ctx, rec_in, seed_step, (const int64_t*)w.tok_buf,
@@ -776,7 +818,7 @@ int ssdk_create(const ssdk_model_cfg* target, const ssdk_model_cfg* draft, const
   if (rt->spec_k < 0 || rt->spec_k > 7) return fail("spec_k=%d out of range [0,7]", rt->spec_k);
   if (rt->max_batch < 1 || rt->max_batch * (rt->spec_k + 1) > kMaxTokens || rt->max_batch > 16)
     return fail("max_batch=%d: need max_batch*(K+1) <= %d and max_batch <= 16", rt->max_batch, kMaxTokens);
-  if (rt->spec_k > 0 && !draft) return fail("spec_k>0 needs a draft model");
+  if (rt->spec_k > 0 && !draft && target->tp_rank == 0) return fail("spec_k>0 needs a draft model on rank 0");
   ssdk_engine* e = new ssdk_engine();
   e->rt = *rt;
   const ssdk_model_cfg* cfgs[2] = {target, draft};
@@ -962,7 +1004,7 @@ int ssdk_spec_step(ssdk_handle h, int batch, const int32_t* ctx_len, const int64
                    const float* temp_q, uint64_t seed, uint64_t step_id, int64_t* out_tokens, int32_t* out_n_accept,
                    int64_t* out_recovery, void* stream) {
   if (!h || !h->finalized) return fail("spec_step: engine not finalized");
-  if (h->rt.spec_k < 1 || !h->model[SSDK_DRAFT].present) return fail("spec_step: engine built without speculation");
+  if (h->rt.spec_k < 1) return fail("spec_step: engine built without speculation");
   cudaStream_t st = (cudaStream_t)stream;
   CKI(fill_step(h, batch, ctx_len, recovery, block_tables_target, block_tables_draft, temp_t, temp_q, seed, step_id));
   if (h->rt.use_graph) {
@@ -997,7 +1039,7 @@ int ssdk_spec_step_stage(ssdk_handle h, int batch, const int32_t* ctx_len, const
 
 int ssdk_spec_step_resident(ssdk_handle h, int batch, void* stream) {
   if (!h || !h->finalized) return fail("spec_step_resident: engine not finalized");
-  if (h->rt.spec_k < 1 || !h->model[SSDK_DRAFT].present) return fail("spec_step: engine built without speculation");
+  if (h->rt.spec_k < 1) return fail("spec_step: engine built without speculation");
   cudaStream_t st = (cudaStream_t)stream;
   if (h->rt.use_graph) {
     cudaGraphExec_t g;
@@ -1067,12 +1109,16 @@ int ssdk_forward_tokens(ssdk_handle h, int which, int batch, int q_len, const in
   f.logits_out = w.logits_last;
   f.logits_ld = m.cfg.vocab;
   CKI(enqueue_forward(h, L, f));
-  if (want_sample) {
+  const bool do_sample = want_sample && m.cfg.tp_rank == 0;
+  if (do_sample) {
     SampleParams sp;
     sp.logits = w.logits_last; sp.ld = m.cfg.vocab; sp.temps = (const float*)(w.step_dev + h->off_tt);
     sp.V = m.cfg.vocab; sp.seed = seed; sp.call_id = step_id * 16ull + 14ull; sp.out = w.out_tok; sp.out_stride = 1;
     sp.partial = w.samp_partial; sp.counters = w.samp_counters; sp.dyn = nullptr; sp.sub = 0;
     CKI(L.go(sample_kernel, dim3(kSampleChunks, batch), dim3(256), 0, sp));
+  }
+  if (want_sample) {
+    if (m.cfg.tp_size > 1) CKN(ncclBroadcast(w.out_tok, w.out_tok, (size_t)batch, ncclInt64, 0, h->comm, st));
     CK(cudaMemcpyAsync(pin_ids, w.out_tok, (size_t)batch * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (out_tokens) memcpy(out_tokens, pin_ids, (size_t)batch * 8);

@@ -45,9 +45,10 @@ class LLMEngine:
             tf, df = infer_model_family(config.model), infer_model_family(config.draft)
             if tf != df:
                 raise AssertionError("target and draft must be of the same model family (llm_engine.py:55-57)")
+        self._workers = None
         if config.num_gpus > 1:
             from ..parallel import launch_tp_engine
-            self.runner, self.draft_cfg = launch_tp_engine(config)
+            self.runner, self.draft_cfg, self._workers = launch_tp_engine(config, model, kwargs)
         else:
             from ..loader import build_runner
             self.runner, self.draft_cfg = build_runner(config)
@@ -64,6 +65,11 @@ class LLMEngine:
         if self._exiting:
             return
         self._exiting = True
+        try:
+            if self._workers is not None:
+                self._workers.close()
+        except Exception:
+            pass
         try:
             self.runner.close()
         except Exception:
@@ -112,6 +118,8 @@ class LLMEngine:
     def generate(self, prompts, sampling_params, use_tqdm: bool = True, stream_callback=None):
         for k in METRICS:
             METRICS[k] = [] if isinstance(METRICS[k], list) else 0
+        if self._workers is not None:  # spawned TP ranks replay the same call (SPMD host engines)
+            self._workers.generate(prompts, sampling_params, stream_callback is not None)
         if not isinstance(sampling_params, list):
             sampling_params = [sampling_params] * len(prompts)
         for p, sp in zip(prompts, sampling_params):

@@ -105,7 +105,7 @@ def kv_blocks_for(config, spec: ModelSpec, tp_size: int, share: float) -> int:
     return max(1, min(fit, want))
 
 
-def build_runner(config, tp_size: int = 1, tp_rank: int = 0, device=None):
+def build_runner(config, tp_size: int = 1, tp_rank: int = 0, device=None, finalize: bool = True):
     device = torch.device(device or "cuda:0")
     torch.cuda.set_device(device)
     tspec = spec_from_config(config.hf_config)
@@ -127,5 +127,6 @@ def build_runner(config, tp_size: int = 1, tp_rank: int = 0, device=None):
     runner.bind_weights(L.TARGET, wt)
     if wd is not None:
         runner.bind_weights(L.DRAFT, wd)
-    runner.finalize()
+    if finalize:
+        runner.finalize()
     return runner, draft_cfg

@@ -163,6 +163,8 @@ class PairRunner:
     def forward_tokens(self, which: int, ids: list[list[int]], ctx_len: list[int], block_tables, temps=None,
                        want_sample: bool = True, seed: int = 0) -> list[int] | None:
         """ModelRunner.run for q_len tokens per sequence appended at ctx_len (prefill chunk or AR decode)."""
+        if self.spec[which] is None:
+            return None  # the draft replica lives on TP rank 0 only (SURVEY §8e); other ranks have nothing to do
         B, Q = len(ids), len(ids[0])
         assert all(len(x) == Q for x in ids)
         ids_a = np.ascontiguousarray(np.array(ids, dtype=np.int64).reshape(-1))
