@@ -275,6 +275,7 @@ struct ssdk_engine {
   std::map<int, int64_t> spec_graph_launches;
   std::map<int, cudaGraphExec_t> spec_graphs_resident;
   int max_ctx_hint = 0;
+  cudaStream_t cap_stream = nullptr;  // graphs are captured here (the caller's stream may be the legacy default stream)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -753,13 +754,15 @@ static int get_spec_graph(ssdk_engine* e, int B, bool host_io, cudaStream_t st, 
     *nlaunch = e->spec_graph_launches[B];
     return 0;
   }
+  (void)st;
+  if (!e->cap_stream) CK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
   Launcher L;
-  L.st = st;
+  L.st = e->cap_stream;
   L.pdl = e->rt.use_pdl != 0;
   cudaGraph_t graph = nullptr;
-  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  CK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
   const int rc = enqueue_spec_step(e, L, B, host_io, !host_io);
-  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
   if (rc != 0) {
     if (graph) cudaGraphDestroy(graph);
     return rc;
@@ -863,6 +866,7 @@ int ssdk_destroy(ssdk_handle h) {
   if (!h) return 0;
   for (auto& kv : h->spec_graphs) cudaGraphExecDestroy(kv.second);
   for (auto& kv : h->spec_graphs_resident) cudaGraphExecDestroy(kv.second);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->pin_in) cudaFreeHost(h->pin_in);
   if (h->pin_out) cudaFreeHost(h->pin_out);
   delete h;
