@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(att_smem);            // [2][64][LDS]
   __nv_bfloat16* sV = sK + 2 * kAttChunk * LDS;                              // [2][64][LDS]
 
+  pdl_launch_dependents();
   pdl_wait();
 
   const int kvh = blockIdx.x, split = blockIdx.y;
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
 // merge split-KV partials: out = sum_s 2^(lse_s - max) o_s / sum_s 2^(lse_s - max)
 __global__ void attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
                                     __nv_bfloat16* __restrict__ out, int n_split, int hd) {
+  pdl_launch_dependents();
   pdl_wait();
   const size_t row = blockIdx.x;  // (token, head)
   float mx = -INFINITY;

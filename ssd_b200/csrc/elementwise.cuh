@@ -52,6 +52,7 @@ __global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __r
                             int max_blocks, int block_size, int batch, int q_len, int pos_offset,
                             int64_t* __restrict__ positions, int32_t* __restrict__ slot_mapping,
                             int32_t* __restrict__ context_lens) {
+  pdl_launch_dependents();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < batch * q_len) {
@@ -90,6 +91,7 @@ struct NormParams {
 __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
   extern __shared__ float rbuf[];  // d floats
   __shared__ float red[32];
+  pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x;
   const int d = p.d;
@@ -162,6 +164,7 @@ struct RopeParams {
 };
 
 __global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
+  pdl_launch_dependents();
   pdl_wait();
   const int m = blockIdx.x;
   const int head = blockIdx.y * 4 + (threadIdx.x >> 5);
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
 // x: [M, 2*ffn] (dense or partials) -> out bf16 [M, ffn]
 // ----------------------------------------------------------------------------------
 __global__ void silu_mul_kernel(GemmOut x, __nv_bfloat16* __restrict__ out, int M, int ffn) {
+  pdl_launch_dependents();
   pdl_wait();
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (idx >= M * ffn) return;
@@ -231,6 +235,7 @@ __global__ void silu_mul_kernel(GemmOut x, __nv_bfloat16* __restrict__ out, int 
 // gather `rows` rows (the last token of each sequence) of a [M, d] matrix: out[b] = x[b*q_len + q_len-1]
 __global__ void gather_last_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int batch,
                                         int q_len, int d) {
+  pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * q_len + q_len - 1) * d);

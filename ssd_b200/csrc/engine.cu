@@ -476,6 +476,7 @@ static int enqueue_tp_allreduce(ssdk_engine* e, Launcher& L, int S, int M, int N
 // [tp, rows, Vs] (all-gather layout) -> [rows, ld] with column r*Vs + v   (torch.cat(parts, -1), embed_head.py:98-99)
 __global__ void unshard_logits_kernel(const bf16* __restrict__ gathered, bf16* __restrict__ out, int tp, int rows, int Vs,
                                       int64_t ld) {
+  pdl_launch_dependents();
   pdl_wait();
   const int64_t n8 = (int64_t)tp * rows * (Vs / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -640,6 +641,7 @@ static void layout_step(ssdk_engine* e) {
 
 // copy the recovery tokens into column 0 of the speculation buffer (speculator_sync.py:38-45)
 __global__ void init_tokens_kernel(const int64_t* __restrict__ recovery, int64_t* __restrict__ tok_buf, int B, int Kp1) {
+  pdl_launch_dependents();
   pdl_wait();
   const int b = threadIdx.x;
   if (b < B) tok_buf[(size_t)b * Kp1] = recovery[b];
@@ -652,6 +654,7 @@ __global__ void advance_kernel(int32_t* __restrict__ ctx, int64_t* __restrict__ 
                                const int64_t* __restrict__ tok_buf, const int32_t* __restrict__ n_accept,
                                const int64_t* __restrict__ recovery_out, int64_t* __restrict__ log_tokens,
                                int32_t* __restrict__ log_len, int B, int Kp1, int log_cap) {
+  pdl_launch_dependents();
   pdl_wait();
   const int b = threadIdx.x;
   if (b < B) {

@@ -213,6 +213,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 // inside the engine the consumer kernels fold this in).
 __global__ void splitk_reduce_kernel(const float* __restrict__ P, __nv_bfloat16* __restrict__ y, int S, int M, int N,
                                      int ldy) {
+  pdl_launch_dependents();
   pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * N) return;

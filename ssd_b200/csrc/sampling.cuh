@@ -65,6 +65,7 @@ struct SampleParams {
 __global__ void __launch_bounds__(256) sample_kernel(SampleParams p) {
   __shared__ ArgMax red[32];
   __shared__ bool is_last;
+  pdl_launch_dependents();
   pdl_wait();
   if (p.dyn) {
     p.seed = p.dyn[0];
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(VerifyParams p) 
   __shared__ int s_n[16], s_flags[16];      // accepted count; bit0 = needs recovery draw, bit1 = adjust
   __shared__ long long s_rec_greedy[16];
   __shared__ bool is_last;
+  pdl_launch_dependents();
   pdl_wait();
   if (p.dyn) {
     p.seed = p.dyn[0];

@@ -6,7 +6,7 @@ weights are built with the "bigram agreement" construction of SURVEY §8(d):
 
   * token embeddings e_t ~ N(0,1)^d (near-orthogonal), lm_head[pi(t)] = e_t  => greedy next token = pi(t);
   * o_proj / down_proj are scaled to ~0 so the residual stream stays the embedding (they are still streamed);
-  * the draft's permutation agrees with the target's on a seeded fraction `alpha` of tokens, so the accepted
+  * the draft knows the target's next token for a seeded fraction `alpha` of tokens (and guesses noise otherwise), so the accepted
     prefix length is Geometric(alpha) truncated at K:  E[tokens/step] = (1 - alpha^(K+1)) / (1 - alpha).
 
 A directory holds config.json (HF layout), ssd_b200_synthetic.json (seed, alpha, role) and a WordLevel
@@ -82,8 +82,7 @@ def permutations(vocab: int, seed: int, alpha: float, device) -> tuple[torch.Ten
     g = torch.Generator(device="cpu").manual_seed(seed * 7919 + 13)
     pi_t = torch.randperm(vocab, generator=g)
     agree = torch.rand(vocab, generator=g) < alpha
-    other = torch.randint(0, vocab, (vocab,), generator=g)
-    pi_d = torch.where(agree, pi_t, other)
+    pi_d = torch.where(agree, pi_t, torch.full_like(pi_t, -1))  # -1: the draft has no idea (its guess will be noise)
     return pi_t.to(device), pi_d.to(device)
 
 
@@ -112,14 +111,16 @@ def generate_weights(spec, meta: dict, device, tp_size: int = 1, tp_rank: int = 
     pi_t, pi_d = permutations(V, seed, alpha, device)
     pi = pi_t if role == "target" else pi_d
     lo, hi = tp_rank * Vs, (tp_rank + 1) * Vs
-    # lm_head[pi(t)] = e_t  <=>  lm_head[v] = e_{pi^-1(v)};  pi_d is not a bijection, use scatter (last write wins)
-    lm_head = torch.zeros(V, d, dtype=bf, device=device) if role != "target" else None
+    # lm_head[pi(t)] = e_t  <=>  lm_head[v] = e_{pi^-1(v)}.  Draft: only the agreeing tokens get their row; the rows
+    # of the others stay zero, so for a disagreeing token the draft's argmax is a noise token != pi_t(t).
     if role == "target":
         inv = torch.empty_like(pi)
         inv[pi] = torch.arange(V, device=device)
         lm_shard = embed_full[inv[lo:hi]].contiguous()
     else:
-        lm_head[pi] = embed_full
+        lm_head = torch.zeros(V, d, dtype=bf, device=device)
+        known = (pi >= 0).nonzero().squeeze(1)
+        lm_head[pi[known]] = embed_full[known]
         lm_shard = lm_head[lo:hi].contiguous()
         del lm_head
     w = {"embed": embed_full[lo:hi].contiguous(), "lm_head": lm_shard,
