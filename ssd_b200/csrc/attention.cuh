@@ -34,6 +34,7 @@ struct AttnParams {
   __nv_bfloat16* out;            // [B*Q, H*hd]
   float* part_o;                 // [B*Q*H, n_split, hd]
   float* part_lse;               // [B*Q*H, n_split]
+  unsigned* counters;            // [B*n_qtiles*KV] arrival tickets (zero on entry, zero again on exit)
   int B, Q, H, KV, block_size, max_blocks, n_split, TQ, n_qtiles;
   float scale_log2;              // softmax scale * log2(e)
 };
@@ -305,6 +306,52 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
       p.part_o[pr * HD + d] = val;
       if (d == 0) p.part_lse[pr] = (l > 0.f) ? mmax + log2f(l) : -INFINITY;
     }
+  }
+  if (p.n_split == 1) return;
+
+  // ---- split-KV merge by the last-arriving split of this (sequence, q-tile, kv head) group ----
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* ctr = p.counters + (size_t)blockIdx.z * p.KV + kvh;
+    const unsigned tk = atomicAdd(ctr, 1u);
+    is_last = (tk == (unsigned)p.n_split - 1u);
+    if (is_last) *ctr = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // splits >= n_active had no chunks: their partials are (o = 0, lse = -inf) and can be skipped
+  const int n_active = (cps > 0) ? min(p.n_split, (nch_total + cps - 1) / cps) : 0;
+  for (int r = warp; r < R; r += kAttThreads / 32) {
+    const int row_q = b * p.Q + qt * p.TQ + r / G;
+    const int head = kvh * G + r % G;
+    const size_t pr = ((size_t)row_q * p.H + head) * p.n_split;
+    const float lse = (lane < n_active) ? __ldcg(p.part_lse + pr + lane) : -INFINITY;  // n_split <= 32
+    const float mx = warp_max(lse);
+    const float wgt = (mx == -INFINITY) ? 0.f : exp2f(lse - mx);
+    const float wsum = warp_sum(wgt);
+    float acc[HD / 32];
+#pragma unroll
+    for (int j = 0; j < HD / 32; ++j) acc[j] = 0.f;
+    for (int s0 = 0; s0 < n_active; s0 += 4) {
+      float v[4][HD / 32];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < HD / 32; ++j)
+          v[u][j] = (s0 + u < n_active) ? __ldcg(p.part_o + (pr + s0 + u) * HD + j * 32 + lane) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float ws = __shfl_sync(0xffffffffu, wgt, (s0 + u) & 31);
+#pragma unroll
+        for (int j = 0; j < HD / 32; ++j) acc[j] += ws * v[u][j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HD / 32; ++j)
+      p.out[((size_t)row_q * p.H + head) * HD + j * 32 + lane] = f2bf(wsum > 0.f ? acc[j] / wsum : 0.f);
   }
 }
 

@@ -222,6 +222,7 @@ struct Workspace {
   bf16 *hidden, *residual, *q, *attn_out, *act, *last_hidden, *dense_tmp;
   float* partials;
   float *att_o, *att_lse;
+  unsigned* att_counters;
   int64_t* positions;
   int32_t *slot_mapping, *context_lens;
   // step state
@@ -336,6 +337,7 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.partial_floats = part;
   w.att_o = (float*)take((size_t)kMaxTokens * Hmax * kAttnMaxSplit * hdmax * 4);
   w.att_lse = (float*)take((size_t)kMaxTokens * Hmax * kAttnMaxSplit * 4);
+  w.att_counters = (unsigned*)take((size_t)kMaxTokens * 64 * 4);
   w.positions = (int64_t*)take(kMaxTokens * 8);
   w.slot_mapping = (int32_t*)take(kMaxTokens * 4);
   w.context_lens = (int32_t*)take(kMaxTokens * 4);
@@ -417,19 +419,17 @@ static int launch_attn(Launcher& L, const AttnParams& p, int hd, int MT, dim3 gr
 }
 
 static int enqueue_attention(Launcher& L, const bf16* q, const bf16* kc, const bf16* vc, const int32_t* bt,
-                             const int32_t* ctx_lens, bf16* out, float* part_o, float* part_lse, int B, int Q, int H,
+                             const int32_t* ctx_lens, bf16* out, float* part_o, float* part_lse, unsigned* counters,
+                             int B, int Q, int H,
                              int KV, int hd, int block_size, int max_blocks, float scale, int TQ, int MT, int nqt,
                              int nsplit) {
   AttnParams a;
   a.q = q; a.k_cache = kc; a.v_cache = vc; a.block_tables = bt; a.context_lens = ctx_lens; a.out = out;
-  a.part_o = part_o; a.part_lse = part_lse;
+  a.part_o = part_o; a.part_lse = part_lse; a.counters = counters;
   a.B = B; a.Q = Q; a.H = H; a.KV = KV; a.block_size = block_size; a.max_blocks = max_blocks;
   a.n_split = nsplit; a.TQ = TQ; a.n_qtiles = nqt;
   a.scale_log2 = scale * 1.4426950408889634f;
-  CKI(launch_attn(L, a, hd, MT, dim3(KV, nsplit, B * nqt)));
-  if (nsplit > 1) CKI(L.go(attn_combine_kernel, dim3(B * Q * H), dim3(std::min(hd, 128)), 0, (const float*)part_o,
-                           (const float*)part_lse, out, nsplit, hd));
-  return 0;
+  return launch_attn(L, a, hd, MT, dim3(KV, nsplit, B * nqt));
 }
 
 static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w, int M, int epi, void* out, int ldo,
@@ -553,7 +553,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
 
     // ---- attention over the paged cache ----
     CKI(enqueue_attention(L, w.q, rp.k_cache, rp.v_cache, f.block_tables, w.context_lens, w.attn_out, w.att_o,
-                          w.att_lse, f.B, f.Q, m.H, m.KV, m.hd, bs, mb, scale, TQ, MT, nqt, nsplit));
+                          w.att_lse, w.att_counters, f.B, f.Q, m.H, m.KV, m.hd, bs, mb, scale, TQ, MT, nqt, nsplit));
 
     // ---- output projection (row-parallel) ----
     CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
@@ -1233,7 +1233,7 @@ static int attn_plan_raw(int H, int KV, int B, int Q, int max_ctx, int* TQ, int*
 
 int64_t ssdk_paged_attn_scratch_bytes(int batch, int q_len, int heads, int head_dim, int max_ctx) {
   (void)max_ctx;
-  return (int64_t)batch * q_len * heads * kAttnMaxSplit * (head_dim + 1) * 4 + 1024;
+  return (int64_t)batch * q_len * heads * kAttnMaxSplit * (head_dim + 1) * 4 + 1024 + 16384;
 }
 
 int ssdk_paged_attn(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_tables,
@@ -1245,10 +1245,12 @@ int ssdk_paged_attn(const void* q, const void* k_cache, const void* v_cache, con
   CKI(init_kernel_attrs());
   int TQ, MT, nqt, nsplit;
   CKI(attn_plan_raw(heads, kv_heads, batch, q_len, block_size * max_blocks_per_seq, &TQ, &MT, &nqt, &nsplit));
-  float* part_o = (float*)scratch;
+  // the first 16 KB of the scratch hold the arrival counters (zero on entry)
+  CK(cudaMemsetAsync(scratch, 0, 16384, L.st));
+  float* part_o = (float*)((uint8_t*)scratch + 16384);
   float* part_lse = part_o + (size_t)batch * q_len * heads * kAttnMaxSplit * head_dim;
   return enqueue_attention(L, (const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache, block_tables, context_lens,
-                           (bf16*)out, part_o, part_lse, batch, q_len, heads, kv_heads, head_dim, block_size,
+                           (bf16*)out, part_o, part_lse, (unsigned*)scratch, batch, q_len, heads, kv_heads, head_dim, block_size,
                            max_blocks_per_seq, scale, TQ, MT, nqt, nsplit);
 }
 
