@@ -236,28 +236,6 @@ SSDK_DEVINL constexpr uint32_t make_umma_idesc_bf16(int M, int N) {
 SSDK_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 SSDK_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// ----------------------------------------------------------------------------------
-// PTX: thread-block clusters / distributed shared memory
-// ----------------------------------------------------------------------------------
-SSDK_DEVINL uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-SSDK_DEVINL void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
-}
-// address of `local_smem` in the shared memory of CTA `rank` of this cluster
-SSDK_DEVINL uint32_t dsmem_addr(const void* local_smem, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(rank));
-  return r;
-}
-SSDK_DEVINL void dsmem_st_v4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 SSDK_DEVINL bool elect_one() {
   uint32_t pred;
   asm volatile(

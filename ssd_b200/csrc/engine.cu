@@ -62,32 +62,19 @@ struct Launcher {
   bool prev_kernel = false;  // the previous op on the stream was one of our kernels
   int64_t count = 0;
 
-  int cluster_y = 1;  // set before go() to launch gridDim.y-wide thread-block clusters (reset after each launch)
-
   template <typename... KArgs, typename... Args>
   int go(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
-    cudaLaunchConfig_t cfg = {};
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (pdl && prev_kernel) {
-      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[na].val.programmaticStreamSerializationAllowed = 1;
-      ++na;
-    }
-    if (cluster_y > 1) {
-      attr[na].id = cudaLaunchAttributeClusterDimension;
-      attr[na].val.clusterDim.x = 1;
-      attr[na].val.clusterDim.y = (unsigned)cluster_y;
-      attr[na].val.clusterDim.z = 1;
-      ++na;
-    }
-    cluster_y = 1;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = na;
+    cfg.numAttrs = (pdl && prev_kernel) ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
     if (e != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e));
     prev_kernel = true;
@@ -161,11 +148,8 @@ static int launch_gemm_inst(Launcher& L, const CUtensorMap& tmW, const CUtensorM
     CK(cudaFuncSetAttribute(gemm_ws_kernel<UN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  if (p.cluster_k && splits > 1) L.cluster_y = splits;
   return L.go(gemm_ws_kernel<UN, EPI>, dim3(tiles, splits), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, tmW, tmX, p);
 }
-// largest split-K a cluster can reduce in rank 0's pipeline smem: (S-1)*128*UMMA_N*4 + 16 KB <= stages*stage_bytes
-static int max_cluster_splits(int umma_n) { return umma_n == 16 ? 8 : (umma_n == 32 ? 4 : 2); }
 static int launch_gemm(Launcher& L, int umma_n, int epi, const CUtensorMap& tmW, const CUtensorMap& tmX,
                        const GemmParams& p, int tiles, int splits) {
 #define SSDK_GEMM_CASE(UN, EP) \
@@ -459,35 +443,33 @@ static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w
   GemmParams p;
   p.out = out; p.M = M; p.N = N_out; p.ldo = ldo; p.num_kb = K / kBlockK;
   int tiles, splits;
-  p.cluster_k = 0;
   if (epi == EPI_SILU) {
     tiles = (N_out + 63) / 64;
+    splits = 1;
     p.tile_rows = 64;
     p.hi_row_offset = N_out;
   } else {
     tiles = (N_out + kTileRows - 1) / kTileRows;
+    splits = (epi == EPI_PARTIAL) ? auto_splits(tiles, p.num_kb) : 1;
     p.tile_rows = kTileRows;
     p.hi_row_offset = 64;
   }
-  splits = auto_splits(tiles, p.num_kb);
-  if (epi != EPI_PARTIAL) {
-    splits = std::min(splits, max_cluster_splits(un));
-    p.cluster_k = splits > 1 ? 1 : 0;
-  }
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
-  splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (epi == EPI_PARTIAL && (size_t)splits * M * N_out > e->ws.partial_floats && out == e->ws.partials)
     return fail("split-K partial buffer too small");
   if (splits_out) *splits_out = splits;
   return launch_gemm(L, un, epi, w.tm, *tmX, p, tiles, splits);
 }
 
-// tensor-parallel row-parallel linears (layers/linear.py:195-199): the local GEMM output (already rounded to bf16 like
-// F.linear) is summed across ranks with an in-graph NCCL bf16 all-reduce, in place.
-static int enqueue_tp_allreduce(ssdk_engine* e, Launcher& L, int M, int N) {
+// y = allreduce_sum(bf16(sum_s partials)) for tensor-parallel row-parallel linears
+// (layers/linear.py:195-199): reduce split-K locally, round to bf16 like F.linear, NCCL bf16 sum.
+static int enqueue_tp_allreduce(ssdk_engine* e, Launcher& L, int S, int M, int N, GemmOut* out) {
   Workspace& w = e->ws;
-  CKN(ncclAllReduce(w.dense_tmp, w.dense_tmp, (size_t)M * N, ncclBfloat16, ncclSum, e->comm, L.st));
+  const int n = M * N;
+  CKI(L.go(splitk_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, (const float*)w.partials, w.dense_tmp, S, M, N, N));
+  CKN(ncclAllReduce(w.dense_tmp, w.dense_tmp, (size_t)n, ncclBfloat16, ncclSum, e->comm, L.st));
   L.barrier_op();
+  out->dense = w.dense_tmp; out->partial = nullptr; out->S = 0; out->M = M; out->N = N;
   return 0;
 }
 
@@ -555,10 +537,10 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, np));
 
     // ---- QKV projection -> RoPE (+qk norm) -> KV store ----
-    // (split-K, when needed to fill the SMs, is reduced inside the GEMM by a thread-block cluster: dense bf16 out)
-    CKI(enqueue_gemm(e, L, w.hidden, lw.qkv, M, EPI_BF16, w.dense_tmp, m.qkv_dim, m.qkv_dim, nullptr));
+    int S = 1;
+    CKI(enqueue_gemm(e, L, w.hidden, lw.qkv, M, EPI_PARTIAL, w.partials, 0, m.qkv_dim, &S));
     RopeParams rp;
-    rp.qkv.dense = w.dense_tmp; rp.qkv.partial = nullptr; rp.qkv.S = 0; rp.qkv.M = M; rp.qkv.N = m.qkv_dim;
+    rp.qkv.dense = nullptr; rp.qkv.partial = w.partials; rp.qkv.S = S; rp.qkv.M = M; rp.qkv.N = m.qkv_dim;
     rp.positions = w.positions; rp.slot_mapping = w.slot_mapping; rp.rope_table = m.rope;
     rp.q_norm_w = m.cfg.qk_norm ? lw.q_norm : nullptr;
     rp.k_norm_w = m.cfg.qk_norm ? lw.k_norm : nullptr;
@@ -574,10 +556,10 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
                           w.att_lse, w.att_counters, f.B, f.Q, m.H, m.KV, m.hd, bs, mb, scale, TQ, MT, nqt, nsplit));
 
     // ---- output projection (row-parallel) ----
-    CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_BF16, w.dense_tmp, m.d, m.d, nullptr));
+    CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
     GemmOut oproj;
-    oproj.dense = w.dense_tmp; oproj.partial = nullptr; oproj.S = 0; oproj.M = M; oproj.N = m.d;
-    if (tp > 1) CKI(enqueue_tp_allreduce(e, L, M, m.d));
+    oproj.dense = nullptr; oproj.partial = w.partials; oproj.S = S; oproj.M = M; oproj.N = m.d;
+    if (tp > 1) CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &oproj));
 
     // ---- post-attention norm ----
     NormParams pn;
@@ -586,11 +568,19 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     pn.y = w.hidden; pn.residual_out = w.residual; pn.d = m.d;
     CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, pn));
 
-    // ---- MLP: gate|up with the fused SiLU*mul epilogue, down projection (row-parallel) ----
-    CKI(enqueue_gemm(e, L, w.hidden, lw.gate_up, M, EPI_SILU, w.act, m.ffn, m.ffn, nullptr));
-    CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_BF16, w.dense_tmp, m.d, m.d, nullptr));
-    prev.dense = w.dense_tmp; prev.partial = nullptr; prev.S = 0; prev.M = M; prev.N = m.d;
-    if (tp > 1) CKI(enqueue_tp_allreduce(e, L, M, m.d));
+    // ---- MLP: gate|up with fused SiLU*mul when the tile count fills the machine ----
+    const int silu_tiles = (m.ffn + 63) / 64;
+    if (silu_tiles >= num_sms() / 2) {
+      CKI(enqueue_gemm(e, L, w.hidden, lw.gate_up, M, EPI_SILU, w.act, m.ffn, m.ffn, nullptr));
+    } else {
+      CKI(enqueue_gemm(e, L, w.hidden, lw.gate_up, M, EPI_PARTIAL, w.partials, 0, 2 * m.ffn, &S));
+      GemmOut gu;
+      gu.dense = nullptr; gu.partial = w.partials; gu.S = S; gu.M = M; gu.N = 2 * m.ffn;
+      CKI(L.go(silu_mul_kernel, dim3((M * m.ffn / 8 + 255) / 256), dim3(256), 0, gu, w.act, M, m.ffn));
+    }
+    CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
+    prev.dense = nullptr; prev.partial = w.partials; prev.S = S; prev.M = M; prev.N = m.d;
+    if (tp > 1) CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &prev));
   }
   // ---- final norm ----
   NormParams fn;
@@ -1164,19 +1154,17 @@ int ssdk_gemm_small_m(const void* x, const void* w, void* y, float* partials, in
   CKI(make_tmap(&tmX, x, M, K, un));
   const int tiles = (N + kTileRows - 1) / kTileRows;
   const int num_kb = K / kBlockK;
-  int S = split_k > 0 ? std::min(split_k, num_kb) : std::min(auto_splits(tiles, num_kb), max_cluster_splits(un));
+  int S = split_k > 0 ? std::min(split_k, num_kb) : auto_splits(tiles, num_kb);
+  if (S > 1 && !partials) return fail("gemm_small_m: split_k=%d needs a partials buffer", S);
   GemmParams p;
   p.M = M; p.N = N; p.ldo = ldy; p.num_kb = num_kb; p.tile_rows = kTileRows; p.hi_row_offset = 64;
   p.kb_per_split = (num_kb + S - 1) / S;
   S = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  if (S <= max_cluster_splits(un)) {  // split-K reduced inside the kernel by a thread-block cluster (DSMEM)
+  if (S == 1) {
     p.out = y;
-    p.cluster_k = S > 1 ? 1 : 0;
-    return launch_gemm(L, un, EPI_BF16, tmW, tmX, p, tiles, S);
+    return launch_gemm(L, un, EPI_BF16, tmW, tmX, p, tiles, 1);
   }
-  if (!partials) return fail("gemm_small_m: split_k=%d needs a partials buffer", S);
   p.out = partials;
-  p.cluster_k = 0;
   CKI(launch_gemm(L, un, EPI_PARTIAL, tmW, tmX, p, tiles, S));
   const int n = M * N;
   return L.go(splitk_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, (const float*)partials, (bf16*)y, S, M, N, ldy);
@@ -1192,14 +1180,9 @@ int ssdk_gemm_gate_up_silu(const void* x, const void* w_gate_up, void* hout, int
   const int un = umma_n_for(M);
   CKI(make_tmap(&tmX, x, M, K, un));
   GemmParams p;
-  p.out = hout; p.M = M; p.N = ffn; p.ldo = ffn; p.num_kb = K / kBlockK;
+  p.out = hout; p.M = M; p.N = ffn; p.ldo = ffn; p.num_kb = K / kBlockK; p.kb_per_split = p.num_kb;
   p.tile_rows = 64; p.hi_row_offset = ffn;
-  const int tiles = (ffn + 63) / 64;
-  int S = std::min(auto_splits(tiles, p.num_kb), max_cluster_splits(un));
-  p.kb_per_split = (p.num_kb + S - 1) / S;
-  S = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  p.cluster_k = S > 1 ? 1 : 0;
-  return launch_gemm(L, un, EPI_SILU, tmW, tmX, p, tiles, S);
+  return launch_gemm(L, un, EPI_SILU, tmW, tmX, p, (ffn + 63) / 64, 1);
 }
 
 int ssdk_rmsnorm(const void* x, const void* residual_in, const void* w, float eps, void* y, void* residual_out, int M,

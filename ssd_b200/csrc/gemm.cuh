@@ -15,12 +15,9 @@
 //     once per forward), X evict-last (re-read by every CTA from L2).
 //   * warp-specialised: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator +
 //     MMA issuer (one lane), warps 2-5 = epilogue (tcgen05.ld -> registers -> global).
-//   * split-K over blockIdx.y fills the 148 SMs when N/128 is small.  The S <= 8 CTAs of a tile are
-//     launched as ONE thread-block cluster: after their MMAs retire, ranks 1..S-1 push their fp32
-//     accumulators into rank 0's (now idle) pipeline shared memory through DSMEM
-//     (st.shared::cluster), rank 0 adds them in rank order (deterministic) and runs the epilogue, so
-//     consumers read a dense bf16 matrix.  (EPI_PARTIAL keeps the old fp32 [S, M, N] global partials
-//     for split counts beyond a cluster.)
+//   * split-K over blockIdx.y fills the 148 SMs when N/128 is small; partial sums go to
+//     an fp32 [S, M, N] buffer which the *consumer* kernel (norm / rope / silu) reduces
+//     in a fixed order, so results are deterministic.
 //   * epilogues: bf16 store, fp32 split-K partial, or fused SiLU(gate)*up where a tile is
 //     64 gate rows + 64 up rows of the packed gate|up matrix (layers/activation.py:11-14).
 //   * PDL: weight tiles of the first kStages are requested BEFORE griddepcontrol.wait, so
@@ -46,7 +43,6 @@ struct GemmParams {
   int kb_per_split;   // k-blocks per blockIdx.y
   int tile_rows;      // output columns per tile: 128 (plain) or 64 (silu)
   int hi_row_offset;  // W row offset of the second 64-row half: 64 (plain) or ffn (silu)
-  int cluster_k;      // 1: the gridDim.y split-K CTAs of a tile form a thread-block cluster and reduce through DSMEM
 };
 
 template <int UMMA_N>
@@ -156,55 +152,18 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       }
       umma_commit(&tmem_full_bar);  // accumulator complete
     }
-  }
-
-  // ===================== epilogue (warps 2..5 hold the accumulator rows) =====================
-  const bool is_epi = warp >= 2;
-  const int q = warp & 3;  // TMEM lane quarter this warp may access
-  const int row = q * 32 + lane;
-  uint32_t r[UMMA_N];
-  if (is_epi) {
+  } else {
+    // ===================== epilogue warps (2..5) =====================
     pdl_wait();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    uint32_t r[UMMA_N];
 #pragma unroll
     for (int c = 0; c < UMMA_N / 16; ++c) tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(q * 32) << 16) + c * 16, r + c * 16);
     tmem_ld_wait();
-  }
 
-  bool do_store = true;
-  if (EPI != EPI_PARTIAL && p.cluster_k && gridDim.y > 1) {
-    // ---- split-K reduction across the cluster through distributed shared memory ----
-    const uint32_t rank = cluster_ctarank();
-    constexpr int kSlotFloats = kTileRows * UMMA_N;
-    float* slots = reinterpret_cast<float*>(smem + 16384);  // [S-1][128][UMMA_N]; [0,16K) is the SiLU exchange area
-    __syncthreads();     // this CTA's MMAs have retired (epilogue warps saw tmem_full): its pipeline smem is idle
-    cluster_sync_all();  // ... and so is rank 0's
-    if (is_epi && rank != 0) {
-      const uint32_t dst = dsmem_addr(slots + (size_t)(rank - 1) * kSlotFloats + row * UMMA_N, 0);
-#pragma unroll
-      for (int c = 0; c < UMMA_N; c += 4)
-        dsmem_st_v4(dst + c * 4, __uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]),
-                    __uint_as_float(r[c + 3]));
-    }
-    cluster_sync_all();  // remote accumulators have landed in rank 0
-    do_store = (rank == 0);
-    if (is_epi && rank == 0) {
-      for (uint32_t s = 1; s < gridDim.y; ++s) {
-        const float4* src = reinterpret_cast<const float4*>(slots + (size_t)(s - 1) * kSlotFloats + row * UMMA_N);
-#pragma unroll
-        for (int c = 0; c < UMMA_N / 4; ++c) {
-          const float4 v = src[c];
-          r[4 * c + 0] = __float_as_uint(__uint_as_float(r[4 * c + 0]) + v.x);
-          r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + v.y);
-          r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + v.z);
-          r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + v.w);
-        }
-      }
-    }
-  }
-
-  if (is_epi && do_store) {
     if (EPI == EPI_BF16) {
       const int n = row_lo + row;
       if (n < p.N) {
