@@ -80,6 +80,31 @@ def load_safetensors_weights(path: str, spec: ModelSpec, device, tp_size: int = 
     return w
 
 
+def shard_packed_weights(w: dict, spec: ModelSpec, tp_size: int, tp_rank: int) -> dict:
+    """Slice full packed weights (tp=1 layout) into rank `tp_rank`'s shard with the reference's rules:
+    qkv / gate_up column-parallel per sub-matrix (layers/linear.py:116-122,148-162), o / down row-parallel
+    (:188-193), embedding / lm_head by vocab rows (embed_head.py:41-47), norms replicated."""
+    H, KV, hd, ffn, V = spec.heads, spec.kv_heads, spec.head_dim, spec.ffn, spec.vocab
+    h, kv, f, vs = H // tp_size, KV // tp_size, ffn // tp_size, V // tp_size
+    r = tp_rank
+    out = {"embed": w["embed"][r * vs:(r + 1) * vs].contiguous(), "lm_head": w["lm_head"][r * vs:(r + 1) * vs].contiguous(),
+           "final_norm": w["final_norm"], "layers": []}
+    for lw in w["layers"]:
+        q, k, v = lw["qkv"].split([H * hd, KV * hd, KV * hd], dim=0)
+        gate, up = lw["gate_up"].chunk(2, dim=0)
+        o = {"input_norm": lw["input_norm"], "post_norm": lw["post_norm"],
+             "qkv": torch.cat([q[r * h * hd:(r + 1) * h * hd], k[r * kv * hd:(r + 1) * kv * hd],
+                               v[r * kv * hd:(r + 1) * kv * hd]]).contiguous(),
+             "o": lw["o"][:, r * h * hd:(r + 1) * h * hd].contiguous(),
+             "gate_up": torch.cat([gate[r * f:(r + 1) * f], up[r * f:(r + 1) * f]]).contiguous(),
+             "down": lw["down"][:, r * f:(r + 1) * f].contiguous()}
+        for k2 in ("q_norm", "k_norm"):
+            if k2 in lw:
+                o[k2] = lw[k2]
+        out["layers"].append(o)
+    return out
+
+
 def load_weights(path: str, spec: ModelSpec, device, tp_size: int = 1, tp_rank: int = 0) -> dict:
     marker = os.path.join(path, "ssd_b200_synthetic.json")
     if os.path.exists(marker):

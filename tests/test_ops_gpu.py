@@ -24,7 +24,7 @@ def _ref_linear(x, w):
 @pytest.mark.parametrize("M,N,K,split", [
     (1, 512, 128, 1), (7, 512, 128, 1), (7, 3072, 2048, 1), (1, 3072, 2048, 0), (7, 4096, 4096, 0),
     (16, 2048, 8192, 0), (7, 4096, 4096, 3), (33, 1024, 512, 1), (64, 1280, 1024, 0), (7, 16032, 2048, 1),
-    (5, 200, 64, 1),
+    (5, 200, 64, 1), (7, 2048, 8192, 8), (7, 1024, 4096, 16), (20, 1024, 2048, 4), (40, 512, 1024, 2),
 ])
 def test_linear_matches_fp64(dev, M, N, K, split):
     from ssd_b200 import ops
