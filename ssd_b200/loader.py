@@ -144,7 +144,7 @@ def build_runner(config, tp_size: int = 1, tp_rank: int = 0, device=None, finali
     config.num_kvcache_blocks = nbt
     draft_cfg = _DraftCfg()
     draft_cfg.num_kvcache_blocks = nbd or nbt
-    runner = PairRunner(tspec, dspec, spec_k=config.speculate_k if config.speculate else 0,
+    runner = PairRunner(tspec, dspec, spec_k=config.speculate_k if config.speculate else 0,  # workers keep K although they hold no draft
                         max_batch=max(1, config.max_num_seqs), block_size=config.kvcache_block_size,
                         max_model_len=config.max_model_len, num_blocks_target=nbt, num_blocks_draft=nbd, device=device,
                         use_graph=config.use_cuda_graph, use_pdl=config.use_pdl, jit_speculate=config.jit_speculate,

@@ -88,7 +88,7 @@ class PairRunner:
 
         tcfg = cfg(target, tp_size, tp_rank)
         dcfg = cfg(draft, 1, 0) if draft is not None else None
-        rt = L.RuntimeCfg(spec_k if draft is not None else 0, max_batch, block_size, self.max_blocks, int(use_graph),
+        rt = L.RuntimeCfg(spec_k, max_batch, block_size, self.max_blocks, int(use_graph),
                           int(use_pdl), int(jit_speculate), 0)
         h = C.c_void_p()
         L.check(self.lib.ssdk_create(C.byref(tcfg), C.byref(dcfg) if dcfg is not None else None, C.byref(rt),

@@ -91,11 +91,16 @@ def test_tp2_spec_steps(use_graph):
     for p in procs:
         p.start()
     res = {}
-    for _ in range(2):
-        rank, status, payload, log = q.get(timeout=300)
-        res[rank] = (status, payload, log)
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        for _ in range(2):
+            rank, status, payload, log = q.get(timeout=150)
+            res[rank] = (status, payload, log)
+            assert status == "ok", f"rank {rank} failed:\n{payload}"
+    finally:
+        for p in procs:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
     for rank, (status, payload, _) in res.items():
         assert status == "ok", f"rank {rank} failed:\n{payload}"
     # the verdict broadcast makes every rank see identical tokens / accept counts / recovery tokens
