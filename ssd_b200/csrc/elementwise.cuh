@@ -193,12 +193,8 @@ struct RopeParams {
   int heads, kv_heads, head_dim;
 };
 
-// one (token, head) pair per warp.  `staged` (optional) holds the already reduced+rounded [M, (H+2KV)*hd] matrix in
-// shared memory (GEMM tail path); otherwise values come from the GEMM output in global memory.
-SSDK_DEVINL float rope_in(const RopeParams& p, const float* staged, int m, int col) {
-  return staged ? staged[(size_t)m * p.qkv.N + col] : gemm_out_at(p.qkv, m, col);
-}
-SSDK_DEVINL void rope_head(const RopeParams& p, int m, int head, int lane, const float* staged = nullptr) {
+// one (token, head) pair per warp
+SSDK_DEVINL void rope_head(const RopeParams& p, int m, int head, int lane) {
   const int H = p.heads, KV = p.kv_heads, hd = p.head_dim, half = hd >> 1;
   const int kind = head < H ? 0 : (head < H + KV ? 1 : 2);  // q, k, v
   const int col0 = head * hd;
@@ -207,7 +203,7 @@ SSDK_DEVINL void rope_head(const RopeParams& p, int m, int head, int lane, const
   if (kind == 2) {
     if (slot < 0) return;
     __nv_bfloat16* dst = p.v_cache + ((size_t)slot * KV + (head - H - KV)) * hd;
-    for (int i = lane; i < hd; i += 32) dst[i] = f2bf(rope_in(p, staged, m, col0 + i));
+    for (int i = lane; i < hd; i += 32) dst[i] = f2bf(gemm_out_at(p.qkv, m, col0 + i));
     return;
   }
   if (kind == 1 && slot < 0) return;
@@ -217,8 +213,8 @@ SSDK_DEVINL void rope_head(const RopeParams& p, int m, int head, int lane, const
   int np = 0;
   float ss = 0.f;
   for (int i = lane; i < half; i += 32, ++np) {
-    x1[np] = rope_in(p, staged, m, col0 + i);
-    x2[np] = rope_in(p, staged, m, col0 + half + i);
+    x1[np] = gemm_out_at(p.qkv, m, col0 + i);
+    x2[np] = gemm_out_at(p.qkv, m, col0 + half + i);
     ss += x1[np] * x1[np] + x2[np] * x2[np];
   }
   const __nv_bfloat16* nw = (kind == 0) ? p.q_norm_w : p.k_norm_w;

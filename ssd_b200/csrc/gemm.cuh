@@ -236,20 +236,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         float* rbuf = reinterpret_cast<float*>(smem);  // pipeline smem is idle: all MMAs of this CTA have retired
         for (int m = 0; m < tail.M; ++m) norm_row(tail.norm, m, rbuf, tail_red);
       } else {
-        // stage the split-K-reduced, bf16-rounded [M, qkv_dim] matrix in (idle) pipeline smem with ONE wave of
-        // batched L2 loads, then rotate / scatter from smem
-        float* xs = reinterpret_cast<float*>(smem);
-        const int total = tail.M * tail.rope.qkv.N;
-        for (int i = threadIdx.x * 8; i < total; i += kGemmThreads * 8) {
-          float f8[8];
-          gemm_out_at8(tail.rope.qkv, i / tail.rope.qkv.N, i % tail.rope.qkv.N, f8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xs[i + j] = f8[j];
-        }
-        __syncthreads();
         const int nheads = tail.rope.heads + 2 * tail.rope.kv_heads;
         for (int idx = warp; idx < tail.M * nheads; idx += kGemmThreads / 32)
-          rope_head(tail.rope, idx / nheads, idx % nheads, lane, xs);
+          rope_head(tail.rope, idx / nheads, idx % nheads, lane);
       }
     }
   }
