@@ -113,8 +113,12 @@ struct NormParams {
   int d;
 };
 
-// one token row; cooperative over the whole thread block (any blockDim.x multiple of 32)
-SSDK_DEVINL void norm_row(const NormParams& p, int m, float* rbuf, float* red) {
+__global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
+  extern __shared__ float rbuf[];  // d floats
+  __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x;
   const int d = p.d;
   const __nv_bfloat16* erow = nullptr;
   bool zero_row = false;
@@ -160,15 +164,6 @@ SSDK_DEVINL void norm_row(const NormParams& p, int m, float* rbuf, float* red) {
       *reinterpret_cast<uint4*>(p.y + (size_t)m * d + i) = pack_bf16x8(o);
     }
   }
-  __syncthreads();  // rbuf / red are reused by the next row
-}
-
-__global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
-  extern __shared__ float rbuf[];  // d floats
-  __shared__ float red[32];
-  pdl_launch_dependents();
-  pdl_wait();
-  norm_row(p, blockIdx.x, rbuf, red);
 }
 
 // ----------------------------------------------------------------------------------
@@ -193,9 +188,14 @@ struct RopeParams {
   int heads, kv_heads, head_dim;
 };
 
-// one (token, head) pair per warp
-SSDK_DEVINL void rope_head(const RopeParams& p, int m, int head, int lane) {
+__global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int m = blockIdx.x;
+  const int head = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   const int H = p.heads, KV = p.kv_heads, hd = p.head_dim, half = hd >> 1;
+  if (head >= H + 2 * KV) return;
   const int kind = head < H ? 0 : (head < H + KV ? 1 : 2);  // q, k, v
   const int col0 = head * hd;
   const int slot = p.slot_mapping[m];
@@ -237,14 +237,6 @@ SSDK_DEVINL void rope_head(const RopeParams& p, int m, int head, int lane) {
     dst[i] = f2bf(x1[t] * c - x2[t] * s);
     dst[half + i] = f2bf(x2[t] * c + x1[t] * s);
   }
-}
-
-__global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int head = blockIdx.y * 4 + (threadIdx.x >> 5);
-  if (head >= p.heads + 2 * p.kv_heads) return;
-  rope_head(p, blockIdx.x, head, threadIdx.x & 31);
 }
 
 // ----------------------------------------------------------------------------------

@@ -139,27 +139,21 @@ static int auto_splits(int tiles, int num_kb) {
   return (num_kb + per - 1) / per;
 }
 
-static TailParams no_tail() {
-  TailParams t;
-  memset(&t, 0, sizeof(t));
-  return t;
-}
-
 template <int UN, int EPI>
 static int launch_gemm_inst(Launcher& L, const CUtensorMap& tmW, const CUtensorMap& tmX, const GemmParams& p, int tiles,
-                            int splits, const TailParams& tail) {
+                            int splits) {
   using Cfg = GemmCfg<UN>;
   static bool attr_set = false;
   if (!attr_set) {
     CK(cudaFuncSetAttribute(gemm_ws_kernel<UN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  return L.go(gemm_ws_kernel<UN, EPI>, dim3(tiles, splits), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, tmW, tmX, p, tail);
+  return L.go(gemm_ws_kernel<UN, EPI>, dim3(tiles, splits), dim3(kGemmThreads), (size_t)Cfg::kSmemBytes, tmW, tmX, p);
 }
 static int launch_gemm(Launcher& L, int umma_n, int epi, const CUtensorMap& tmW, const CUtensorMap& tmX,
-                       const GemmParams& p, int tiles, int splits, const TailParams& tail) {
+                       const GemmParams& p, int tiles, int splits) {
 #define SSDK_GEMM_CASE(UN, EP) \
-  if (umma_n == UN && epi == EP) return launch_gemm_inst<UN, EP>(L, tmW, tmX, p, tiles, splits, tail);
+  if (umma_n == UN && epi == EP) return launch_gemm_inst<UN, EP>(L, tmW, tmX, p, tiles, splits);
   SSDK_GEMM_CASE(16, EPI_BF16) SSDK_GEMM_CASE(16, EPI_PARTIAL) SSDK_GEMM_CASE(16, EPI_SILU)
   SSDK_GEMM_CASE(32, EPI_BF16) SSDK_GEMM_CASE(32, EPI_PARTIAL) SSDK_GEMM_CASE(32, EPI_SILU)
   SSDK_GEMM_CASE(64, EPI_BF16) SSDK_GEMM_CASE(64, EPI_PARTIAL) SSDK_GEMM_CASE(64, EPI_SILU)
@@ -229,7 +223,6 @@ struct Workspace {
   float* partials;
   float *att_o, *att_lse;
   unsigned* att_counters;
-  unsigned* tail_counters;  // [4] last-CTA tickets of the GEMM tail ops
   int64_t* positions;
   int32_t *slot_mapping, *context_lens;
   // step state
@@ -345,7 +338,6 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.att_o = (float*)take((size_t)kMaxTokens * Hmax * kAttnMaxSplit * hdmax * 4);
   w.att_lse = (float*)take((size_t)kMaxTokens * Hmax * kAttnMaxSplit * 4);
   w.att_counters = (unsigned*)take((size_t)kMaxTokens * 64 * 4);
-  w.tail_counters = (unsigned*)take(64);
   w.positions = (int64_t*)take(kMaxTokens * 8);
   w.slot_mapping = (int32_t*)take(kMaxTokens * 4);
   w.context_lens = (int32_t*)take(kMaxTokens * 4);
@@ -441,7 +433,7 @@ static int enqueue_attention(Launcher& L, const bf16* q, const bf16* kc, const b
 }
 
 static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w, int M, int epi, void* out, int ldo,
-                        int N_out, int* splits_out, const TailParams* tail = nullptr) {
+                        int N_out, int* splits_out) {
   CKI(weight_tmap(w));
   const int K = (int)w.cols;
   if (K % kBlockK) return fail("GEMM K=%d not a multiple of 64", K);
@@ -466,7 +458,7 @@ static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w
   if (epi == EPI_PARTIAL && (size_t)splits * M * N_out > e->ws.partial_floats && out == e->ws.partials)
     return fail("split-K partial buffer too small");
   if (splits_out) *splits_out = splits;
-  return launch_gemm(L, un, epi, w.tm, *tmX, p, tiles, splits, tail ? *tail : no_tail());
+  return launch_gemm(L, un, epi, w.tm, *tmX, p, tiles, splits);
 }
 
 // y = allreduce_sum(bf16(sum_s partials)) for tensor-parallel row-parallel linears
@@ -515,32 +507,14 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
 
   GemmOut prev;  // output of the previous row-parallel GEMM feeding the next norm
   prev.dense = nullptr; prev.partial = nullptr; prev.S = 0; prev.M = M; prev.N = m.d;
-  // Small consumers (the draft's M=1 norm / RoPE: a few thousand elements) run as a TAIL of the producing split-K GEMM
-  // (last-arriving CTA) instead of a kernel of their own; large ones (M=K+1 rows of the target) keep their own grid.
-  auto tail_fits = [&](int n_out, int num_kb) {
-    const int tiles = (n_out + kTileRows - 1) / kTileRows;
-    return (size_t)M * n_out * auto_splits(tiles, num_kb) <= 65536;
-  };
-  const bool rope_tail = tail_fits(m.qkv_dim, m.d / kBlockK);
-  const bool o_tail = tp == 1 && tail_fits(m.d, m.H * m.hd / kBlockK);
-  const bool down_tail = tp == 1 && tail_fits(m.d, m.ffn / kBlockK);
-  bool input_norm_done = false;  // the previous layer's down GEMM already produced hidden/residual for this layer
-
-  auto norm_params = [&](const GemmOut& x, const bf16* weight, bool write_residual) {
-    NormParams np;
-    memset(&np, 0, sizeof(np));
-    np.x = x; np.residual_in = w.residual; np.w = weight; np.eps = m.cfg.rms_eps; np.y = w.hidden;
-    np.residual_out = write_residual ? w.residual : nullptr; np.d = m.d;
-    return np;
-  };
 
   for (int l = 0; l < m.cfg.layers; ++l) {
     LayerW& lw = m.layers[l];
     // ---- input norm (layer 0: embedding gather, no residual) ----
+    NormParams np;
+    memset(&np, 0, sizeof(np));
+    np.eps = m.cfg.rms_eps; np.d = m.d; np.w = lw.input_norm; np.y = w.hidden; np.residual_out = w.residual;
     if (l == 0) {
-      NormParams np;
-      memset(&np, 0, sizeof(np));
-      np.eps = m.cfg.rms_eps; np.d = m.d; np.w = lw.input_norm; np.y = w.hidden; np.residual_out = w.residual;
       if (tp == 1) {
         np.ids = f.ids; np.ids_stride = f.ids_stride; np.embed = m.embed.ptr;
         np.vocab_start = 0; np.vocab_rows = m.vocab_local;
@@ -556,14 +530,17 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
         L.barrier_op();
         np.x.dense = w.dense_tmp; np.x.S = 0; np.x.M = M; np.x.N = m.d;
       }
-      CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, np));
-    } else if (!input_norm_done) {
-      CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, norm_params(prev, lw.input_norm, true)));
+    } else {
+      np.x = prev;
+      np.residual_in = w.residual;
     }
+    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, np));
 
     // ---- QKV projection -> RoPE (+qk norm) -> KV store ----
+    int S = 1;
+    CKI(enqueue_gemm(e, L, w.hidden, lw.qkv, M, EPI_PARTIAL, w.partials, 0, m.qkv_dim, &S));
     RopeParams rp;
-    rp.qkv.dense = nullptr; rp.qkv.partial = w.partials; rp.qkv.M = M; rp.qkv.N = m.qkv_dim;
+    rp.qkv.dense = nullptr; rp.qkv.partial = w.partials; rp.qkv.S = S; rp.qkv.M = M; rp.qkv.N = m.qkv_dim;
     rp.positions = w.positions; rp.slot_mapping = w.slot_mapping; rp.rope_table = m.rope;
     rp.q_norm_w = m.cfg.qk_norm ? lw.q_norm : nullptr;
     rp.k_norm_w = m.cfg.qk_norm ? lw.k_norm : nullptr;
@@ -572,41 +549,24 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     rp.k_cache = m.k_cache + (size_t)l * cache_layer_stride;
     rp.v_cache = m.v_cache + (size_t)l * cache_layer_stride;
     rp.heads = m.H; rp.kv_heads = m.KV; rp.head_dim = m.hd;
-    {
-      const int tiles = (m.qkv_dim + kTileRows - 1) / kTileRows;
-      rp.qkv.S = auto_splits(tiles, m.d / kBlockK);  // same value enqueue_gemm picks
-    }
-    int S = 1;
-    if (rope_tail) {
-      TailParams t = no_tail();
-      t.kind = TAIL_ROPE; t.M = M; t.counter = w.tail_counters + 0; t.rope = rp;
-      CKI(enqueue_gemm(e, L, w.hidden, lw.qkv, M, EPI_PARTIAL, w.partials, 0, m.qkv_dim, &S, &t));
-      if (S != rp.qkv.S) return fail("internal: split-K plan mismatch (%d vs %d)", S, rp.qkv.S);
-    } else {
-      CKI(enqueue_gemm(e, L, w.hidden, lw.qkv, M, EPI_PARTIAL, w.partials, 0, m.qkv_dim, &S));
-      rp.qkv.S = S;
-      CKI(L.go(rope_store_kernel, dim3(M, (m.H + 2 * m.KV + 3) / 4), dim3(128), 0, rp));
-    }
+    CKI(L.go(rope_store_kernel, dim3(M, (m.H + 2 * m.KV + 3) / 4), dim3(128), 0, rp));
 
     // ---- attention over the paged cache ----
     CKI(enqueue_attention(L, w.q, rp.k_cache, rp.v_cache, f.block_tables, w.context_lens, w.attn_out, w.att_o,
                           w.att_lse, w.att_counters, f.B, f.Q, m.H, m.KV, m.hd, bs, mb, scale, TQ, MT, nqt, nsplit));
 
-    // ---- output projection (row-parallel) + post-attention norm ----
+    // ---- output projection (row-parallel) ----
+    CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
     GemmOut oproj;
-    oproj.dense = nullptr; oproj.partial = w.partials; oproj.M = M; oproj.N = m.d;
-    oproj.S = auto_splits((m.d + kTileRows - 1) / kTileRows, m.H * m.hd / kBlockK);
-    if (o_tail) {
-      TailParams t = no_tail();
-      t.kind = TAIL_NORM; t.M = M; t.counter = w.tail_counters + 1; t.norm = norm_params(oproj, lw.post_norm, true);
-      CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PARTIAL, w.partials, 0, m.d, &S, &t));
-      if (S != oproj.S) return fail("internal: split-K plan mismatch (%d vs %d)", S, oproj.S);
-    } else {
-      CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
-      oproj.S = S;
-      if (tp > 1) CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &oproj));
-      CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, norm_params(oproj, lw.post_norm, true)));
-    }
+    oproj.dense = nullptr; oproj.partial = w.partials; oproj.S = S; oproj.M = M; oproj.N = m.d;
+    if (tp > 1) CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &oproj));
+
+    // ---- post-attention norm ----
+    NormParams pn;
+    memset(&pn, 0, sizeof(pn));
+    pn.x = oproj; pn.residual_in = w.residual; pn.w = lw.post_norm; pn.eps = m.cfg.rms_eps;
+    pn.y = w.hidden; pn.residual_out = w.residual; pn.d = m.d;
+    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, pn));
 
     // ---- MLP: gate|up with fused SiLU*mul when the tile count fills the machine ----
     const int silu_tiles = (m.ffn + 63) / 64;
@@ -618,28 +578,16 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
       gu.dense = nullptr; gu.partial = w.partials; gu.S = S; gu.M = M; gu.N = 2 * m.ffn;
       CKI(L.go(silu_mul_kernel, dim3((M * m.ffn / 8 + 255) / 256), dim3(256), 0, gu, w.act, M, m.ffn));
     }
-
-    // ---- down projection (row-parallel); its consumer is the NEXT layer's input norm (or the final norm) ----
-    prev.dense = nullptr; prev.partial = w.partials; prev.M = M; prev.N = m.d;
-    prev.S = auto_splits((m.d + kTileRows - 1) / kTileRows, m.ffn / kBlockK);
-    const bool last = (l + 1 == m.cfg.layers);
-    if (down_tail) {
-      TailParams t = no_tail();
-      t.kind = TAIL_NORM; t.M = M; t.counter = w.tail_counters + 2;
-      t.norm = norm_params(prev, last ? m.final_norm : m.layers[l + 1].input_norm, !last);
-      CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_PARTIAL, w.partials, 0, m.d, &S, &t));
-      if (S != prev.S) return fail("internal: split-K plan mismatch (%d vs %d)", S, prev.S);
-      input_norm_done = true;
-    } else {
-      CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
-      prev.S = S;
-      if (tp > 1) CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &prev));
-      input_norm_done = false;
-    }
+    CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
+    prev.dense = nullptr; prev.partial = w.partials; prev.S = S; prev.M = M; prev.N = m.d;
+    if (tp > 1) CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &prev));
   }
-  // ---- final norm (unless the last down GEMM already ran it as its tail) ----
-  if (!input_norm_done)
-    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, norm_params(prev, m.final_norm, false)));
+  // ---- final norm ----
+  NormParams fn;
+  memset(&fn, 0, sizeof(fn));
+  fn.x = prev; fn.residual_in = w.residual; fn.w = m.final_norm; fn.eps = m.cfg.rms_eps; fn.y = w.hidden;
+  fn.residual_out = nullptr; fn.d = m.d;
+  CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, fn));
 
   // ---- lm_head ----
   if (f.logits_mode != 0) {
@@ -1214,10 +1162,10 @@ int ssdk_gemm_small_m(const void* x, const void* w, void* y, float* partials, in
   S = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (S == 1) {
     p.out = y;
-    return launch_gemm(L, un, EPI_BF16, tmW, tmX, p, tiles, 1, no_tail());
+    return launch_gemm(L, un, EPI_BF16, tmW, tmX, p, tiles, 1);
   }
   p.out = partials;
-  CKI(launch_gemm(L, un, EPI_PARTIAL, tmW, tmX, p, tiles, S, no_tail()));
+  CKI(launch_gemm(L, un, EPI_PARTIAL, tmW, tmX, p, tiles, S));
   const int n = M * N;
   return L.go(splitk_reduce_kernel, dim3((n + 255) / 256), dim3(256), 0, (const float*)partials, (bf16*)y, S, M, N, ldy);
 }
@@ -1234,7 +1182,7 @@ int ssdk_gemm_gate_up_silu(const void* x, const void* w_gate_up, void* hout, int
   GemmParams p;
   p.out = hout; p.M = M; p.N = ffn; p.ldo = ffn; p.num_kb = K / kBlockK; p.kb_per_split = p.num_kb;
   p.tile_rows = 64; p.hi_row_offset = ffn;
-  return launch_gemm(L, un, EPI_SILU, tmW, tmX, p, (ffn + 63) / 64, 1, no_tail());
+  return launch_gemm(L, un, EPI_SILU, tmW, tmX, p, (ffn + 63) / 64, 1);
 }
 
 int ssdk_rmsnorm(const void* x, const void* residual_in, const void* w, float eps, void* y, void* residual_out, int M,

@@ -25,7 +25,6 @@
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
-#include "elementwise.cuh"
 
 namespace ssdk {
 
@@ -46,19 +45,6 @@ struct GemmParams {
   int hi_row_offset;  // W row offset of the second 64-row half: 64 (plain) or ffn (silu)
 };
 
-// Optional work the LAST-arriving CTA of a split-K GEMM performs on the complete result, so that tiny consumers
-// (the draft model's M=1 norm / RoPE) do not cost a kernel boundary of their own: every CTA publishes its fp32
-// partial tile, takes a ticket, and the CTA that draws the last ticket sees all partials (L2-resident) and runs
-// the consumer for all M rows with its 192 threads.
-enum GemmTail { TAIL_NONE = 0, TAIL_NORM = 1, TAIL_ROPE = 2 };
-struct TailParams {
-  int kind;
-  int M;
-  unsigned* counter;  // zero on entry, reset by the last CTA
-  NormParams norm;
-  RopeParams rope;
-};
-
 template <int UMMA_N>
 struct GemmCfg {
   static constexpr int kABytes = kTileRows * kBlockK * 2;  // 16384
@@ -71,8 +57,7 @@ struct GemmCfg {
 
 template <int UMMA_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
-gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, GemmParams p,
-               const __grid_constant__ TailParams tail) {
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, GemmParams p) {
   using Cfg = GemmCfg<UMMA_N>;
   constexpr int kStages = Cfg::kStages;
 
@@ -215,30 +200,6 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           const float h = (g / (1.0f + __expf(-g))) * u;
           out[(size_t)m * p.ldo + n] = f2bf(h);
         }
-      }
-    }
-  }
-
-  if (EPI == EPI_PARTIAL && tail.kind != TAIL_NONE) {
-    __shared__ int s_last;
-    __shared__ float tail_red[32];
-    __threadfence();  // this thread's partial stores are visible device-wide before the ticket is drawn
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned tk = atomicAdd(tail.counter, 1u);
-      s_last = (tk == gridDim.x * gridDim.y - 1u) ? 1 : 0;
-      if (s_last) *tail.counter = 0u;
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      if (tail.kind == TAIL_NORM) {
-        float* rbuf = reinterpret_cast<float*>(smem);  // pipeline smem is idle: all MMAs of this CTA have retired
-        for (int m = 0; m < tail.M; ++m) norm_row(tail.norm, m, rbuf, tail_red);
-      } else {
-        const int nheads = tail.rope.heads + 2 * tail.rope.kv_heads;
-        for (int idx = warp; idx < tail.M * nheads; idx += kGemmThreads / 32)
-          rope_head(tail.rope, idx / nheads, idx % nheads, lane);
       }
     }
   }
