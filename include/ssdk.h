@@ -177,6 +177,10 @@ int ssdk_forward_tokens(ssdk_handle h, int which, int batch, int q_len,
 const void* ssdk_logits_p(ssdk_handle h);
 const void* ssdk_logits_q(ssdk_handle h);
 const void* ssdk_logits_last(ssdk_handle h);
+/* Debug timeline: CTA 0 of every kernel appends (kernel id, %globaltimer ns) to dev_buf (uint64 [cap][2]) right
+ * after its grid dependency resolves; replaces the reference's SSD_PROFILE perf_counter prints (engine/step.py:92-161).
+ * dev_buf = NULL turns tracing off. */
+int ssdk_debug_trace(void* dev_buf, int cap);
 /* number of kernels this library launched (or replayed inside graphs) so far */
 int64_t ssdk_launch_count(ssdk_handle h);
 

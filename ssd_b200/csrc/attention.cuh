@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
 
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_ATTN);
 
   const int kvh = blockIdx.x, split = blockIdx.y;
   const int b = blockIdx.z / p.n_qtiles, qt = blockIdx.z % p.n_qtiles;

@@ -236,6 +236,29 @@ SSDK_DEVINL constexpr uint32_t make_umma_idesc_bf16(int M, int N) {
 SSDK_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 SSDK_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------------
+// Timeline tracing (debug aid, off by default): CTA (0,0,0) of every kernel records
+// (kernel id, %globaltimer) right after its grid dependency resolves.  Because each kernel's
+// griddepcontrol.wait returns when its predecessor has fully completed, consecutive records are
+// the real, PDL-overlapped, per-kernel increments of the critical path inside a graph replay —
+// something ncu's serialised replay cannot show.  Enabled with ssdk_debug_trace().
+// ----------------------------------------------------------------------------------
+__device__ unsigned long long* g_trace_buf = nullptr;  // [cap][2] = (id, time ns)
+__device__ unsigned g_trace_cap = 0;
+__device__ unsigned g_trace_n = 0;
+enum { TR_PREP = 1, TR_NORM, TR_GEMM, TR_ROPE, TR_ATTN, TR_SAMPLE, TR_VERIFY, TR_MISC };
+SSDK_DEVINL void trace_mark(int id) {
+  if (g_trace_buf == nullptr) return;
+  if ((blockIdx.x | blockIdx.y | blockIdx.z) != 0) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned slot = atomicAdd(&g_trace_n, 1u);
+  if (slot < g_trace_cap) {
+    g_trace_buf[2 * slot] = (unsigned long long)id;
+    g_trace_buf[2 * slot + 1] = t;
+  }
+}
+
 SSDK_DEVINL bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -79,6 +79,7 @@ __global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __r
                             int32_t* __restrict__ context_lens) {
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_PREP);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < batch * q_len) {
     const int b = i / q_len, j = i - b * q_len;
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
   __shared__ float red[32];
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_NORM);
   const int m = blockIdx.x;
   const int d = p.d;
   const __nv_bfloat16* erow = nullptr;
@@ -191,6 +193,7 @@ struct RopeParams {
 __global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_ROPE);
   const int m = blockIdx.x;
   const int head = blockIdx.y * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
 __global__ void silu_mul_kernel(GemmOut x, __nv_bfloat16* __restrict__ out, int M, int ffn) {
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_MISC);
   const int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (idx >= M * ffn) return;
   const int m = idx / ffn, n = idx - m * ffn;
@@ -262,6 +266,7 @@ __global__ void gather_last_rows_kernel(const __nv_bfloat16* __restrict__ x, __n
                                         int q_len, int d) {
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_MISC);
   const int b = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(x + ((size_t)b * q_len + q_len - 1) * d);
   uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b * d);

@@ -1134,6 +1134,16 @@ int ssdk_forward_tokens(ssdk_handle h, int which, int batch, int q_len, const in
   return 0;
 }
 
+// debug: route the kernels' timeline marks into `dev_buf` (uint64 [cap][2]); dev_buf = NULL disables tracing
+int ssdk_debug_trace(void* dev_buf, int cap) {
+  unsigned long long* p = (unsigned long long*)dev_buf;
+  unsigned c = (unsigned)cap, zero = 0;
+  CK(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
+  CK(cudaMemcpyToSymbol(g_trace_cap, &c, sizeof(c)));
+  CK(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));
+  return 0;
+}
+
 const void* ssdk_logits_p(ssdk_handle h) { return h ? h->ws.logits_p : nullptr; }
 const void* ssdk_logits_q(ssdk_handle h) { return h ? h->ws.logits_q : nullptr; }
 const void* ssdk_logits_last(ssdk_handle h) { return h ? h->ws.logits_last : nullptr; }

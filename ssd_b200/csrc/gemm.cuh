@@ -115,6 +115,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         tma_load_2d(a_s + Cfg::kABytes / 2, &tmW, &full_bar[i], k, row_hi, kEvictFirst);
       }
       pdl_wait();  // X is produced by the previous kernel
+      trace_mark(TR_GEMM);
       for (int i = 0; i < pre; ++i) {
         uint8_t* b_s = smem + i * Cfg::kStageBytes + Cfg::kABytes;
         tma_load_2d(b_s, &tmX, &full_bar[i], (kb0 + i) * kBlockK, 0, kEvictLast);

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) sample_kernel(SampleParams p) {
   __shared__ bool is_last;
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_SAMPLE);
   if (p.dyn) {
     p.seed = p.dyn[0];
     p.call_id = p.dyn[1] * 16ull + (uint64_t)p.sub;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(VerifyParams p) 
   __shared__ bool is_last;
   pdl_launch_dependents();
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_VERIFY);
   if (p.dyn) {
     p.seed = p.dyn[0];
     p.call_id = p.dyn[1] * 16ull + (uint64_t)p.sub;

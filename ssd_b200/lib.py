@@ -67,6 +67,7 @@ SIGNATURES: dict[str, tuple] = {
     "ssdk_logits_p": (VP, [VP]),
     "ssdk_logits_q": (VP, [VP]),
     "ssdk_logits_last": (VP, [VP]),
+    "ssdk_debug_trace": (C.c_int, [VP, C.c_int]),
     "ssdk_launch_count": (C.c_int64, [VP]),
     "ssdk_gemm_small_m": (C.c_int, [VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, VP]),
     "ssdk_gemm_gate_up_silu": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]),
