@@ -137,19 +137,35 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
   for (int i = 0; i < ND; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
 
+  // A 64-token chunk never straddles a page when block_size % 64 == 0 (the reference uses 256): one block-table
+  // lookup per chunk instead of one dependent global load per 16-byte segment.
+  const bool page_aligned = (p.block_size % kAttChunk) == 0;
   auto load_chunk = [&](int ch, int stage) {
     const int base = ch * kAttChunk;
     __nv_bfloat16* dk = sK + stage * kAttChunk * LDS;
     __nv_bfloat16* dv = sV + stage * kAttChunk * LDS;
+    int chunk_blk = -1, chunk_off = 0;
+    if (page_aligned) {
+      chunk_blk = bt[base / p.block_size];
+      chunk_off = base % p.block_size;
+    }
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < kAttChunk * SEG; idx += kAttThreads) {
       const int tok = idx / SEG, seg = idx - tok * SEG;
       const int pos = base + tok;
       bool valid = pos < kv_max;
       size_t off = 0;
       if (valid) {
-        const int blk = bt[pos / p.block_size];
+        int blk, in_blk;
+        if (page_aligned) {
+          blk = chunk_blk;
+          in_blk = chunk_off + tok;
+        } else {
+          blk = bt[pos / p.block_size];
+          in_blk = pos % p.block_size;
+        }
         valid = blk >= 0;
-        off = (((size_t)blk * p.block_size + pos % p.block_size) * p.KV + kvh) * HD + seg * 8;
+        off = (((size_t)blk * p.block_size + in_blk) * p.KV + kvh) * HD + seg * 8;
       }
       cp_async16(dk + tok * LDS + seg * 8, p.k_cache + off, valid);
       cp_async16(dv + tok * LDS + seg * 8, p.v_cache + off, valid);
@@ -325,6 +341,8 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
   __threadfence();
   // splits >= n_active had no chunks: their partials are (o = 0, lse = -inf) and can be skipped
   const int n_active = (cps > 0) ? min(p.n_split, (nch_total + cps - 1) / cps) : 0;
+  // phase 1: per-(row, split) weights 2^(lse - max) / sum into smem — one wave of loads for the whole group
+  float* sW = reinterpret_cast<float*>(att_smem);  // [R][n_split]   (K/V staging is dead by now)
   for (int r = warp; r < R; r += kAttThreads / 32) {
     const int row_q = b * p.Q + qt * p.TQ + r / G;
     const int head = kvh * G + r % G;
@@ -333,26 +351,32 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
     const float mx = warp_max(lse);
     const float wgt = (mx == -INFINITY) ? 0.f : exp2f(lse - mx);
     const float wsum = warp_sum(wgt);
-    float acc[HD / 32];
+    if (lane < p.n_split) sW[r * p.n_split + lane] = (wsum > 0.f) ? wgt / wsum : 0.f;
+  }
+  __syncthreads();
+  // phase 2: every thread owns float4 slices of the output; all of its partial loads are issued before use
+  constexpr int V4 = HD / 4;
+  for (int idx = threadIdx.x; idx < R * V4; idx += kAttThreads) {
+    const int r = idx / V4, d4 = idx - r * V4;
+    const int row_q = b * p.Q + qt * p.TQ + r / G;
+    const int head = kvh * G + r % G;
+    const size_t pr = ((size_t)row_q * p.H + head) * p.n_split;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < n_active; s0 += 8) {
+      float4 v[8];
 #pragma unroll
-    for (int j = 0; j < HD / 32; ++j) acc[j] = 0.f;
-    for (int s0 = 0; s0 < n_active; s0 += 4) {
-      float v[4][HD / 32];
+      for (int u = 0; u < 8; ++u)
+        v[u] = (s0 + u < n_active) ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (pr + s0 + u) * HD) + d4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int j = 0; j < HD / 32; ++j)
-          v[u][j] = (s0 + u < n_active) ? __ldcg(p.part_o + (pr + s0 + u) * HD + j * 32 + lane) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float ws = __shfl_sync(0xffffffffu, wgt, (s0 + u) & 31);
-#pragma unroll
-        for (int j = 0; j < HD / 32; ++j) acc[j] += ws * v[u][j];
+      for (int u = 0; u < 8; ++u) {
+        const float ws = (s0 + u < n_active) ? sW[r * p.n_split + s0 + u] : 0.f;
+        acc.x += ws * v[u].x; acc.y += ws * v[u].y; acc.z += ws * v[u].z; acc.w += ws * v[u].w;
       }
     }
-#pragma unroll
-    for (int j = 0; j < HD / 32; ++j)
-      p.out[((size_t)row_q * p.H + head) * HD + j * 32 + lane] = f2bf(wsum > 0.f ? acc[j] / wsum : 0.f);
+    __nv_bfloat16* dst = p.out + ((size_t)row_q * p.H + head) * HD + d4 * 4;
+    *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(acc.x, acc.y);
+    *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(acc.z, acc.w);
   }
 }
 

@@ -19,18 +19,18 @@ struct GemmOut {
 };
 
 // Split-K partials are summed in the fixed order s = 0..S-1 (deterministic), but the loads are issued in
-// batches of 4 so that the reduction costs ~S/4 L2 round trips instead of S.
+// batches of 8 so that the reduction costs ~S/8 L2 round trips instead of S.
 SSDK_DEVINL float gemm_out_at(const GemmOut& g, int m, int n) {
   if (g.S == 0) return bf2f(g.dense[(size_t)m * g.N + n]);
   const float* base = g.partial + (size_t)m * g.N + n;
   const size_t stride = (size_t)g.M * g.N;
   float acc = 0.f;
-  for (int s0 = 0; s0 < g.S; s0 += 4) {
-    float v[4];
+  for (int s0 = 0; s0 < g.S; s0 += 8) {
+    float v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = (s0 + u < g.S) ? __ldcg(base + (size_t)(s0 + u) * stride) : 0.f;
+    for (int u = 0; u < 8; ++u) v[u] = (s0 + u < g.S) ? __ldcg(base + (size_t)(s0 + u) * stride) : 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc += v[u];
+    for (int u = 0; u < 8; ++u) acc += v[u];
   }
   return bf16_round(acc);
 }
@@ -45,10 +45,10 @@ SSDK_DEVINL void gemm_out_at8(const GemmOut& g, int m, int n, float* f) {
   for (int i = 0; i < 8; ++i) f[i] = 0.f;
   const float* base = g.partial + (size_t)m * g.N + n;
   const size_t stride = (size_t)g.M * g.N;
-  for (int s0 = 0; s0 < g.S; s0 += 4) {
-    float4 a[4], b[4];
+  for (int s0 = 0; s0 < g.S; s0 += 8) {
+    float4 a[8], b[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       if (s0 + u < g.S) {
         const float4* p = reinterpret_cast<const float4*>(base + (size_t)(s0 + u) * stride);
         a[u] = __ldcg(p);
@@ -59,7 +59,7 @@ SSDK_DEVINL void gemm_out_at8(const GemmOut& g, int m, int n, float* f) {
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       f[0] += a[u].x; f[1] += a[u].y; f[2] += a[u].z; f[3] += a[u].w;
       f[4] += b[u].x; f[5] += b[u].y; f[6] += b[u].z; f[7] += b[u].w;
     }
