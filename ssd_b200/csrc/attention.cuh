@@ -324,81 +324,61 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
       if (d == 0) p.part_lse[pr] = (l > 0.f) ? mmax + log2f(l) : -INFINITY;
     }
   }
-  if (p.n_split == 1) return;
+}
 
-  // ---- split-KV merge by the last-arriving split of this (sequence, q-tile, kv head) group ----
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned* ctr = p.counters + (size_t)blockIdx.z * p.KV + kvh;
-    const unsigned tk = atomicAdd(ctr, 1u);
-    is_last = (tk == (unsigned)p.n_split - 1u);
-    if (is_last) *ctr = 0u;
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // splits >= n_active had no chunks: their partials are (o = 0, lse = -inf) and can be skipped
+// merge split-KV partials: out = sum_s 2^(lse_s - max) o_s / sum_s 2^(lse_s - max).
+// One CTA per (token, head) row, HD/4 threads, each owning one float4 of the output.  Only the splits that had
+// chunks (n_active, recomputed from context_lens with the attention kernel's formula) are read, and every thread
+// issues all of its loads before using them, so the merge costs ~2 L2 round trips whatever n_split is.
+__global__ void attn_combine_kernel(AttnParams p, int hd) {
+  __shared__ float sw[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_ATTN);
+  const size_t row = blockIdx.x;  // (token, head)
+  const int tok = (int)(row / p.H);
+  const int b = tok / p.Q, j = tok - b * p.Q;
+  const int qt = j / p.TQ;
+  const int tq = min(p.TQ, p.Q - qt * p.TQ);
+  const int kv_max = p.context_lens[b] - p.Q + qt * p.TQ + tq;
+  const int nch_total = (kv_max + kAttChunk - 1) / kAttChunk;
+  const int cps = (nch_total + p.n_split - 1) / p.n_split;
   const int n_active = (cps > 0) ? min(p.n_split, (nch_total + cps - 1) / cps) : 0;
-  // phase 1: per-(row, split) weights 2^(lse - max) / sum into smem — one wave of loads for the whole group
-  float* sW = reinterpret_cast<float*>(att_smem);  // [R][n_split]   (K/V staging is dead by now)
-  for (int r = warp; r < R; r += kAttThreads / 32) {
-    const int row_q = b * p.Q + qt * p.TQ + r / G;
-    const int head = kvh * G + r % G;
-    const size_t pr = ((size_t)row_q * p.H + head) * p.n_split;
-    const float lse = (lane < n_active) ? __ldcg(p.part_lse + pr + lane) : -INFINITY;  // n_split <= 32
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const float lse = (lane < n_active) ? __ldcg(p.part_lse + row * p.n_split + lane) : -INFINITY;
     const float mx = warp_max(lse);
     const float wgt = (mx == -INFINITY) ? 0.f : exp2f(lse - mx);
     const float wsum = warp_sum(wgt);
-    if (lane < p.n_split) sW[r * p.n_split + lane] = (wsum > 0.f) ? wgt / wsum : 0.f;
+    sw[lane] = (wsum > 0.f) ? wgt / wsum : 0.f;
   }
+  const int d4 = threadIdx.x;
+  float4 v[8];
+  const bool mine = d4 < hd / 4;
+  // first batch of partial loads is issued before the weights are ready
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    v[u] = (mine && u < n_active) ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (row * p.n_split + u) * hd) + d4)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  // phase 2: every thread owns float4 slices of the output; all of its partial loads are issued before use
-  constexpr int V4 = HD / 4;
-  for (int idx = threadIdx.x; idx < R * V4; idx += kAttThreads) {
-    const int r = idx / V4, d4 = idx - r * V4;
-    const int row_q = b * p.Q + qt * p.TQ + r / G;
-    const int head = kvh * G + r % G;
-    const size_t pr = ((size_t)row_q * p.H + head) * p.n_split;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < n_active; s0 += 8) {
-      float4 v[8];
+  if (!mine) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < n_active; s0 += 8) {
+    if (s0 > 0) {
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        v[u] = (s0 + u < n_active) ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (pr + s0 + u) * HD) + d4)
+        v[u] = (s0 + u < n_active) ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (row * p.n_split + s0 + u) * hd) + d4)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float ws = (s0 + u < n_active) ? sW[r * p.n_split + s0 + u] : 0.f;
-        acc.x += ws * v[u].x; acc.y += ws * v[u].y; acc.z += ws * v[u].z; acc.w += ws * v[u].w;
-      }
+    for (int u = 0; u < 8; ++u) {
+      const float ws = (s0 + u < n_active) ? sw[s0 + u] : 0.f;
+      acc.x += ws * v[u].x; acc.y += ws * v[u].y; acc.z += ws * v[u].z; acc.w += ws * v[u].w;
     }
-    __nv_bfloat16* dst = p.out + ((size_t)row_q * p.H + head) * HD + d4 * 4;
-    *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(acc.x, acc.y);
-    *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(acc.z, acc.w);
   }
-}
-
-// merge split-KV partials: out = sum_s 2^(lse_s - max) o_s / sum_s 2^(lse_s - max)
-__global__ void attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
-                                    __nv_bfloat16* __restrict__ out, int n_split, int hd) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const size_t row = blockIdx.x;  // (token, head)
-  float mx = -INFINITY;
-  for (int s = 0; s < n_split; ++s) mx = fmaxf(mx, __ldcg(part_lse + row * n_split + s));
-  for (int d = threadIdx.x; d < hd; d += blockDim.x) {
-    float acc = 0.f, wsum = 0.f;
-    if (mx != -INFINITY) {
-      for (int s = 0; s < n_split; ++s) {
-        const float w = exp2f(__ldcg(part_lse + row * n_split + s) - mx);
-        acc += w * __ldcg(part_o + (row * n_split + s) * hd + d);
-        wsum += w;
-      }
-    }
-    out[row * hd + d] = f2bf(wsum > 0.f ? acc / wsum : 0.f);
-  }
+  __nv_bfloat16* dst = p.out + row * hd + d4 * 4;
+  *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(acc.x, acc.y);
+  *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(acc.z, acc.w);
 }
 
 }  // namespace ssdk

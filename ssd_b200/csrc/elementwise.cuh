@@ -100,8 +100,29 @@ __global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __r
 //   residual_out = bf16(r)
 //   y          = bf16(r * rsqrt(mean(r^2) + eps) * w)        (layers/layernorm.py:64-88, compiled form)
 // ----------------------------------------------------------------------------------
+// One-shot all-reduce input (tensor parallel): every rank's bf16 contribution sits in THIS rank's symmetric
+// buffer (pushed there by ar_publish_kernel over NVLink); flags[r] holds the last epoch rank r has published.
+struct SymmIn {
+  const uint8_t* base;    // this rank's symmetric buffer; nullptr = not used
+  const unsigned* epoch;  // local: epoch of the all-reduce to consume (written by the local ar_publish_kernel)
+  int n_ranks;
+  unsigned slot_bytes;
+};
+constexpr int kSymmFlagsBytes = 1024;  // 8 flags, one per 128-byte line
+constexpr int kSymmMaxRanks = 8;
+
+SSDK_DEVINL unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SSDK_DEVINL void st_release_sys_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 struct NormParams {
   GemmOut x;
+  SymmIn symm;
   const int64_t* ids;
   int ids_stride;
   const __nv_bfloat16* embed;
@@ -122,6 +143,20 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
   if (threadIdx.x == 0) trace_mark(TR_NORM);
   const int m = blockIdx.x;
   const int d = p.d;
+  // ---- one-shot all-reduce input: wait until every rank has pushed its contribution of this epoch ----
+  const uint8_t* symm_slots = nullptr;
+  if (p.symm.base) {
+    const unsigned e = __ldcg(p.symm.epoch);
+    if (threadIdx.x < p.symm.n_ranks) {
+      const unsigned* flag = reinterpret_cast<const unsigned*>(p.symm.base + threadIdx.x * 128);
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_sys_u32(flag) - e) < 0) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+      }
+    }
+    __syncthreads();
+    symm_slots = p.symm.base + kSymmFlagsBytes + (size_t)(e & 1u) * kSymmMaxRanks * p.symm.slot_bytes;
+  }
   const __nv_bfloat16* erow = nullptr;
   bool zero_row = false;
   if (p.ids) {
@@ -132,7 +167,27 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
   float ss = 0.f;
   for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
     float x[8];
-    if (p.ids) {
+    if (symm_slots) {
+      // sum the ranks' bf16 contributions in rank order (identical on every rank), fp32 accumulate, one bf16 rounding
+      uint4 v[kSymmMaxRanks];
+#pragma unroll
+      for (int r = 0; r < kSymmMaxRanks; ++r)
+        if (r < p.symm.n_ranks)
+          v[r] = __ldcg(reinterpret_cast<const uint4*>(symm_slots + (size_t)r * p.symm.slot_bytes) + ((size_t)m * d + i) / 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = 0.f;
+#pragma unroll
+      for (int r = 0; r < kSymmMaxRanks; ++r) {
+        if (r < p.symm.n_ranks) {
+          float c[8];
+          unpack_bf16x8(v[r], c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] += c[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = bf16_round(x[j]);
+    } else if (p.ids) {
       if (zero_row) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = 0.f;
@@ -165,6 +220,71 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
       for (int j = 0; j < 8; ++j) o[j] = rbuf[i + j] * rstd * w[j];
       *reinterpret_cast<uint4*>(p.y + (size_t)m * d + i) = pack_bf16x8(o);
     }
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// ar_publish_kernel — first half of the one-shot all-reduce that replaces dist.all_reduce on the row-parallel
+// boundaries (layers/linear.py:195-199, embed_head.py:56).  Each rank reduces its split-K partials (or gathers its
+// masked embedding rows), rounds to bf16 exactly like the reference's per-rank F.linear output, and PUSHES the
+// result over NVLink into slot[parity][my_rank] of EVERY rank's symmetric buffer; the last CTA then releases
+// flag[my_rank] = epoch on every rank (st.release.sys).  The consumer (add_rmsnorm_kernel with SymmIn) acquires the
+// flags, sums the slots in rank order and continues with residual add + RMSNorm — no NCCL call, no extra pass.
+// Slots are double-buffered by epoch parity; a rank cannot run two epochs ahead of a peer because it needs that
+// peer's flag of the previous epoch first.
+// ----------------------------------------------------------------------------------
+struct ArPublishParams {
+  GemmOut x;
+  const int64_t* ids;  // embedding mode when non-null
+  int ids_stride;
+  const __nv_bfloat16* embed;
+  int vocab_start, vocab_rows;
+  int M, d, n_ranks, rank;
+  uint8_t* peer[kSymmMaxRanks];
+  unsigned slot_bytes;
+  unsigned* epoch;   // local: last published epoch
+  unsigned* ticket;  // local, zero on entry/exit
+};
+
+__global__ void __launch_bounds__(256) ar_publish_kernel(ArPublishParams p) {
+  __shared__ bool is_last;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) trace_mark(TR_MISC);
+  const unsigned e = __ldcg(p.epoch) + 1u;
+  const size_t slot_off = kSymmFlagsBytes + ((size_t)(e & 1u) * kSymmMaxRanks + p.rank) * p.slot_bytes;
+  const int total = p.M * p.d;
+  for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 8; idx < total; idx += gridDim.x * blockDim.x * 8) {
+    const int m = idx / p.d, i = idx - m * p.d;
+    float x[8];
+    if (p.ids) {
+      const long long id = p.ids[(size_t)m * p.ids_stride] - p.vocab_start;
+      if (id < 0 || id >= p.vocab_rows) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+      } else {
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(p.embed + (size_t)id * p.d + i), x);
+      }
+    } else {
+      gemm_out_at8(p.x, m, i, x);
+    }
+    const uint4 v = pack_bf16x8(x);
+#pragma unroll
+    for (int r = 0; r < kSymmMaxRanks; ++r)
+      if (r < p.n_ranks) *(reinterpret_cast<uint4*>(p.peer[r] + slot_off) + idx / 8) = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned tk = atomicAdd(p.ticket, 1u);
+    is_last = (tk == gridDim.x - 1u);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    *p.ticket = 0u;
+    __threadfence_system();
+    for (int r = 0; r < p.n_ranks; ++r) st_release_sys_u32(reinterpret_cast<unsigned*>(p.peer[r] + p.rank * 128), e);
+    *p.epoch = e;
   }
 }
 

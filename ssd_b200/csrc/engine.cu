@@ -223,6 +223,7 @@ struct Workspace {
   float* partials;
   float *att_o, *att_lse;
   unsigned* att_counters;
+  unsigned* ar_state;  // [0] epoch of the last published all-reduce, [1] publish ticket
   int64_t* positions;
   int32_t *slot_mapping, *context_lens;
   // step state
@@ -276,7 +277,11 @@ struct ssdk_engine {
   std::map<int, int64_t> spec_graph_launches;
   std::map<int, cudaGraphExec_t> spec_graphs_resident;
   int max_ctx_hint = 0;
-  cudaStream_t cap_stream = nullptr;  // graphs are captured here (the caller's stream may be the legacy default stream)
+  cudaStream_t cap_stream = nullptr;
+  // one-shot all-reduce over NVLink symmetric memory (optional; NCCL is used when not bound)
+  int symm_n = 0;
+  uint8_t* symm_peer[kSymmMaxRanks] = {nullptr};
+  unsigned symm_slot_bytes = 0;  // graphs are captured here (the caller's stream may be the legacy default stream)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -338,6 +343,7 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.att_o = (float*)take((size_t)kMaxTokens * Hmax * kAttnMaxSplit * hdmax * 4);
   w.att_lse = (float*)take((size_t)kMaxTokens * Hmax * kAttnMaxSplit * 4);
   w.att_counters = (unsigned*)take((size_t)kMaxTokens * 64 * 4);
+  w.ar_state = (unsigned*)take(64);
   w.positions = (int64_t*)take(kMaxTokens * 8);
   w.slot_mapping = (int32_t*)take(kMaxTokens * 4);
   w.context_lens = (int32_t*)take(kMaxTokens * 4);
@@ -429,7 +435,9 @@ static int enqueue_attention(Launcher& L, const bf16* q, const bf16* kc, const b
   a.B = B; a.Q = Q; a.H = H; a.KV = KV; a.block_size = block_size; a.max_blocks = max_blocks;
   a.n_split = nsplit; a.TQ = TQ; a.n_qtiles = nqt;
   a.scale_log2 = scale * 1.4426950408889634f;
-  return launch_attn(L, a, hd, MT, dim3(KV, nsplit, B * nqt));
+  CKI(launch_attn(L, a, hd, MT, dim3(KV, nsplit, B * nqt)));
+  if (nsplit > 1) CKI(L.go(attn_combine_kernel, dim3(B * Q * H), dim3(32), 0, a, hd));
+  return 0;
 }
 
 static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w, int M, int epi, void* out, int ldo,
@@ -463,6 +471,32 @@ static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w
 
 // y = allreduce_sum(bf16(sum_s partials)) for tensor-parallel row-parallel linears
 // (layers/linear.py:195-199): reduce split-K locally, round to bf16 like F.linear, NCCL bf16 sum.
+static SymmIn symm_in(ssdk_engine* e) {
+  SymmIn s;
+  s.base = e->symm_peer[e->model[SSDK_TARGET].cfg.tp_rank];
+  s.epoch = e->ws.ar_state;
+  s.n_ranks = e->symm_n;
+  s.slot_bytes = e->symm_slot_bytes;
+  return s;
+}
+// first half of the one-shot all-reduce: reduce split-K locally, push bf16 to every rank, release flags
+static int enqueue_ar_publish(ssdk_engine* e, Launcher& L, const GemmOut* x, const NormParams* embed_src, int M, int d) {
+  Model& m = e->model[SSDK_TARGET];
+  ArPublishParams ap;
+  memset(&ap, 0, sizeof(ap));
+  if (x) ap.x = *x;
+  if (embed_src) {
+    ap.ids = embed_src->ids; ap.ids_stride = embed_src->ids_stride; ap.embed = embed_src->embed;
+    ap.vocab_start = embed_src->vocab_start; ap.vocab_rows = embed_src->vocab_rows;
+  }
+  ap.M = M; ap.d = d; ap.n_ranks = e->symm_n; ap.rank = m.cfg.tp_rank;
+  for (int r = 0; r < e->symm_n; ++r) ap.peer[r] = e->symm_peer[r];
+  ap.slot_bytes = e->symm_slot_bytes;
+  ap.epoch = e->ws.ar_state; ap.ticket = e->ws.ar_state + 1;
+  const int n8 = M * d / 8;
+  return L.go(ar_publish_kernel, dim3(std::max(1, std::min((n8 + 255) / 256, num_sms()))), dim3(256), 0, ap);
+}
+
 static int enqueue_tp_allreduce(ssdk_engine* e, Launcher& L, int S, int M, int N, GemmOut* out) {
   Workspace& w = e->ws;
   const int n = M * N;
@@ -505,6 +539,8 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
   CKI(attn_plan(m, f.B, f.Q, &TQ, &MT, &nqt, &nsplit, e->max_ctx_hint));
   const float scale = 1.0f / sqrtf((float)m.hd);
 
+  const bool use_symm = tp > 1 && e->symm_n == tp;
+  bool prev_symm = false;
   GemmOut prev;  // output of the previous row-parallel GEMM feeding the next norm
   prev.dense = nullptr; prev.partial = nullptr; prev.S = 0; prev.M = M; prev.N = m.d;
 
@@ -524,14 +560,20 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
         memset(&ep, 0, sizeof(ep));
         ep.ids = f.ids; ep.ids_stride = f.ids_stride; ep.embed = m.embed.ptr;
         ep.vocab_start = m.cfg.tp_rank * m.vocab_local; ep.vocab_rows = m.vocab_local;
-        ep.eps = m.cfg.rms_eps; ep.d = m.d; ep.residual_out = w.dense_tmp;  // y = null: gather only
-        CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, ep));
-        CKN(ncclAllReduce(w.dense_tmp, w.dense_tmp, (size_t)M * m.d, ncclBfloat16, ncclSum, e->comm, L.st));
-        L.barrier_op();
-        np.x.dense = w.dense_tmp; np.x.S = 0; np.x.M = M; np.x.N = m.d;
+        if (use_symm) {
+          CKI(enqueue_ar_publish(e, L, nullptr, &ep, M, m.d));
+          np.symm = symm_in(e);
+        } else {
+          ep.eps = m.cfg.rms_eps; ep.d = m.d; ep.residual_out = w.dense_tmp;  // y = null: gather only
+          CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, ep));
+          CKN(ncclAllReduce(w.dense_tmp, w.dense_tmp, (size_t)M * m.d, ncclBfloat16, ncclSum, e->comm, L.st));
+          L.barrier_op();
+          np.x.dense = w.dense_tmp; np.x.S = 0; np.x.M = M; np.x.N = m.d;
+        }
       }
     } else {
       np.x = prev;
+      if (prev_symm) np.symm = symm_in(e);
       np.residual_in = w.residual;
     }
     CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, np));
@@ -559,12 +601,21 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
     GemmOut oproj;
     oproj.dense = nullptr; oproj.partial = w.partials; oproj.S = S; oproj.M = M; oproj.N = m.d;
-    if (tp > 1) CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &oproj));
+    bool oproj_symm = false;
+    if (tp > 1) {
+      if (use_symm) {
+        CKI(enqueue_ar_publish(e, L, &oproj, nullptr, M, m.d));
+        oproj_symm = true;
+      } else {
+        CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &oproj));
+      }
+    }
 
     // ---- post-attention norm ----
     NormParams pn;
     memset(&pn, 0, sizeof(pn));
     pn.x = oproj; pn.residual_in = w.residual; pn.w = lw.post_norm; pn.eps = m.cfg.rms_eps;
+    if (oproj_symm) pn.symm = symm_in(e);
     pn.y = w.hidden; pn.residual_out = w.residual; pn.d = m.d;
     CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, pn));
 
@@ -580,12 +631,20 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     }
     CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
     prev.dense = nullptr; prev.partial = w.partials; prev.S = S; prev.M = M; prev.N = m.d;
-    if (tp > 1) CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &prev));
+    if (tp > 1) {
+      if (use_symm) {
+        CKI(enqueue_ar_publish(e, L, &prev, nullptr, M, m.d));
+        prev_symm = true;
+      } else {
+        CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &prev));
+      }
+    }
   }
   // ---- final norm ----
   NormParams fn;
   memset(&fn, 0, sizeof(fn));
   fn.x = prev; fn.residual_in = w.residual; fn.w = m.final_norm; fn.eps = m.cfg.rms_eps; fn.y = w.hidden;
+  if (prev_symm) fn.symm = symm_in(e);
   fn.residual_out = nullptr; fn.d = m.d;
   CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, fn));
 
@@ -948,12 +1007,23 @@ int ssdk_set_nccl_comm(ssdk_handle h, void* nccl_comm) {
   return 0;
 }
 int64_t ssdk_symm_bytes(ssdk_handle h) {
-  (void)h;
-  return 0;
+  if (!h) return fail("null handle");
+  const Model& m = h->model[SSDK_TARGET];
+  if (m.cfg.tp_size <= 1) return 0;
+  const int64_t slot = (int64_t)kMaxTokens * m.d * 2;
+  return kSymmFlagsBytes + 2 * kSymmMaxRanks * slot;
 }
 int ssdk_bind_symm(ssdk_handle h, void* const* peer_ptrs, int n_peers) {
-  (void)h; (void)peer_ptrs; (void)n_peers;
-  return fail("symmetric-memory all-reduce is not built yet (NCCL path is used)");
+  if (!h || !peer_ptrs) return fail("bind_symm: null argument");
+  const Model& m = h->model[SSDK_TARGET];
+  if (n_peers != m.cfg.tp_size || n_peers > kSymmMaxRanks) return fail("bind_symm: %d peers, tp_size %d", n_peers, m.cfg.tp_size);
+  for (int r = 0; r < n_peers; ++r) {
+    if (!peer_ptrs[r]) return fail("bind_symm: null peer pointer %d", r);
+    h->symm_peer[r] = (uint8_t*)peer_ptrs[r];
+  }
+  h->symm_n = n_peers;
+  h->symm_slot_bytes = (unsigned)((size_t)kMaxTokens * m.d * 2);
+  return 0;
 }
 
 int ssdk_finalize(ssdk_handle h, void* stream) {

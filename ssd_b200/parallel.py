@@ -66,6 +66,35 @@ def create_nccl_comm(world: int, rank: int, group=None) -> int:
     return comm.value
 
 
+def bind_symmetric_memory(runner, world: int, rank: int, group=None) -> bool:
+    """Allocate the NVLink symmetric buffer of the one-shot all-reduce (torch symmetric memory: cuMem + peer mapping),
+    rendezvous with the other ranks and hand every rank's mapped pointer to libssdk (ssdk_bind_symm).  Returns False
+    (the engine then keeps the in-graph NCCL all-reduce) when symmetric memory is unavailable or disabled with
+    SSD_B200_NO_SYMM=1."""
+    if os.environ.get("SSD_B200_NO_SYMM") == "1":
+        return False
+    from . import lib as L
+    nbytes = int(runner.lib.ssdk_symm_bytes(runner.h))
+    if nbytes <= 0:
+        return False
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=runner.device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+        ptrs = [int(hdl.buffer_ptrs[r]) for r in range(world)]
+        torch.cuda.synchronize()
+        dist.barrier(group)  # every rank has zeroed its flags before anyone publishes
+    except Exception as exc:  # noqa: BLE001
+        if rank == 0:
+            print(f"[ssd_b200] symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL all-reduce", flush=True)
+        return False
+    arr = (C.c_void_p * world)(*ptrs)
+    L.check(runner.lib.ssdk_bind_symm(runner.h, arr, world), "ssdk_bind_symm")
+    runner._keep.extend([buf, hdl])
+    return True
+
+
 # --------------------------------------------------------------------------------------------- engines
 def _ensure_pg(world: int, rank: int, port: int | None = None) -> None:
     if dist.is_initialized():
@@ -73,7 +102,8 @@ def _ensure_pg(world: int, rank: int, port: int | None = None) -> None:
     if "MASTER_ADDR" in os.environ and port is None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     else:
-        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+        dist.init_process_group("cpu:gloo,cuda:nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank,
+                                device_id=torch.device("cuda", torch.cuda.current_device()))
 
 
 def build_tp_rank(config, world: int, rank: int, local_rank: int, port: int | None = None):
@@ -84,6 +114,7 @@ def build_tp_rank(config, world: int, rank: int, local_rank: int, port: int | No
     comm = create_nccl_comm(world, rank)
     runner, draft_cfg = build_runner(config, tp_size=world, tp_rank=rank, device=f"cuda:{local_rank}", finalize=False)
     runner.set_nccl_comm(comm)
+    runner.symm = bind_symmetric_memory(runner, world, rank)
     runner.finalize()
     # all ranks must agree on the number of KV blocks so that the SPMD schedulers stay identical
     nb = torch.tensor([config.num_kvcache_blocks, draft_cfg.num_kvcache_blocks], dtype=torch.int64,

@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _rank_main(rank, world, port, use_graph, q):
+def _rank_main(rank, world, port, use_graph, use_symm, q):
     import torch.distributed as dist
     from oracle.model import ModelCfg, OracleModel, random_weights
     from oracle.spec import SpecSession, check_greedy_step, contiguous_block_tables
@@ -27,7 +27,8 @@ def _rank_main(rank, world, port, use_graph, q):
     from ssd_b200.runner import ModelSpec, PairRunner
     try:
         torch.cuda.set_device(rank)
-        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank)
+        dist.init_process_group("cpu:gloo,cuda:nccl", init_method=f"tcp://127.0.0.1:{port}", world_size=world, rank=rank,
+                                device_id=torch.device("cuda", rank))
         comm = create_nccl_comm(world, rank)
         K, B, bs, mb = 4, 2, 64, 3
         tc = ModelCfg(hidden=256, layers=2, heads=4, kv_heads=2, head_dim=64, ffn=512, vocab=1024, max_pos=256)
@@ -45,6 +46,9 @@ def _rank_main(rank, world, port, use_graph, q):
         if rank == 0:
             r.bind_weights(L.DRAFT, to(wd))
         r.set_nccl_comm(comm)
+        if use_symm:
+            from ssd_b200.parallel import bind_symmetric_memory
+            assert bind_symmetric_memory(r, world, rank), "symmetric memory could not be set up"
         r.finalize()
         bt = contiguous_block_tables(B, mb)
         bts = [bt[b].tolist() for b in range(B)]
@@ -79,15 +83,15 @@ def _rank_main(rank, world, port, use_graph, q):
         q.put((rank, "fail", traceback.format_exc(), None))
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_tp2_spec_steps(use_graph):
+@pytest.mark.parametrize("use_graph,use_symm", [(False, False), (True, False), (False, True), (True, True)])
+def test_tp2_spec_steps(use_graph, use_symm):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, use_graph, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, use_graph, use_symm, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = {}

@@ -11,11 +11,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ssd_b200 import lib as L, synth  # noqa: E402
 from ssd_b200.llm import LLM  # noqa: E402
 
+import torch.distributed as dist  # noqa: E402
+
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 workload = sys.argv[1] if len(sys.argv) > 1 else "8b"
 shapes = {"8b": ("llama-3.1-8b", "llama-3.2-1b"), "70b": ("llama-3.1-70b", "llama-3.2-1b")}[workload]
 root = tempfile.mkdtemp()
 llm = LLM(synth.make_model_dir(root, shapes[0], "target"), speculate=True, draft=synth.make_model_dir(root, shapes[1], "draft"),
-          speculate_k=6, max_num_seqs=1, max_model_len=4096, jit_speculate=True, use_pdl=("--no-pdl" not in sys.argv))
+          speculate_k=6, num_gpus=world, max_num_seqs=1, max_model_len=4096, jit_speculate=True, use_pdl=("--no-pdl" not in sys.argv))
 r = llm.runner
 random.seed(0)
 prompt = [random.randint(0, 10000) for _ in range(128)]
@@ -28,10 +34,14 @@ for _ in range(3):
 torch.cuda.synchronize()
 cap = 4096
 buf = torch.zeros(cap, 2, dtype=torch.int64, device="cuda")
+if world > 1:
+    dist.barrier()
 L.check(r.lib.ssdk_debug_trace(buf.data_ptr(), cap))
 r.step_resident(1)
 torch.cuda.synchronize()
 L.check(r.lib.ssdk_debug_trace(None, 0))
+if rank != 0:
+    sys.exit(0)
 t = buf.cpu()
 n = int((t[:, 0] != 0).sum())
 names = {1: "prep", 2: "norm", 3: "gemm", 4: "rope", 5: "attn", 6: "sample", 7: "verify", 8: "misc"}
