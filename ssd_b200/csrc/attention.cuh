@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
   const int cps = (nch_total + p.n_split - 1) / p.n_split;
   const int ch_begin = split * cps;
   const int ch_end = min(nch_total, ch_begin + cps);
+  // splits without chunks own no partial: attn_combine_kernel only reads the first ceil(nch_total / cps) splits
+  if (p.n_split > 1 && ch_begin >= ch_end) return;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -296,31 +298,35 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
     }
   }
   __syncthreads();
-  // one (row, column) pair per loop iteration: rows 0..R-1, columns 0..HD-1
-  for (int idx = threadIdx.x; idx < R * HD; idx += kAttThreads) {
-    const int r = idx / HD, d = idx - r * HD;
+  // one (row, 4 columns) slice per loop iteration: rows 0..R-1, columns 0..HD-1
+  for (int idx = threadIdx.x; idx < R * (HD / 4); idx += kAttThreads) {
+    const int r = idx / (HD / 4), d = (idx - r * (HD / 4)) * 4;
     const int mt = r >> 4, rr = r & 15;
     float mmax = -INFINITY;
 #pragma unroll
     for (int sl = 0; sl < TSL; ++sl) mmax = fmaxf(mmax, sO[((sl * MT + mt) * 16 + rr) * LDO + HD]);
-    float acc = 0.f, l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f;
     if (mmax != -INFINITY) {
 #pragma unroll
       for (int sl = 0; sl < TSL; ++sl) {
         const float* w = sO + ((sl * MT + mt) * 16 + rr) * LDO;
         const float wgt = exp2f(w[HD] - mmax);
-        acc += w[d] * wgt;
+        acc.x += w[d] * wgt; acc.y += w[d + 1] * wgt; acc.z += w[d + 2] * wgt; acc.w += w[d + 3] * wgt;
         l += w[HD + 1] * wgt;
       }
     }
     const int row_q = b * p.Q + qt * p.TQ + r / G;
     const int head = kvh * G + r % G;
-    const float val = (l > 0.f) ? acc / l : 0.f;
+    const float inv = (l > 0.f) ? 1.f / l : 0.f;
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     if (p.n_split == 1) {
-      p.out[((size_t)row_q * p.H + head) * HD + d] = f2bf(val);
+      __nv_bfloat16* dst = p.out + ((size_t)row_q * p.H + head) * HD + d;
+      *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(acc.x, acc.y);
+      *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(acc.z, acc.w);
     } else {
       const size_t pr = ((size_t)row_q * p.H + head) * p.n_split + split;
-      p.part_o[pr * HD + d] = val;
+      *reinterpret_cast<float4*>(p.part_o + pr * HD + d) = acc;
       if (d == 0) p.part_lse[pr] = (l > 0.f) ? mmax + log2f(l) : -INFINITY;
     }
   }
