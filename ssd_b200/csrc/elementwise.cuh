@@ -76,7 +76,7 @@ SSDK_DEVINL void gemm_out_at8(const GemmOut& g, int m, int n, float* f) {
 __global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __restrict__ block_tables,
                             int max_blocks, int block_size, int batch, int q_len, int pos_offset,
                             int64_t* __restrict__ positions, int32_t* __restrict__ slot_mapping,
-                            int32_t* __restrict__ context_lens) {
+                            int32_t* __restrict__ context_lens, unsigned* __restrict__ fwd_seq) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(TR_PREP);
@@ -89,6 +89,7 @@ __global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __r
     slot_mapping[i] = (blk < 0) ? -1 : blk * block_size + pos % block_size;
   }
   if (i < batch) context_lens[i] = ctx0[i] + pos_offset + q_len;
+  if (fwd_seq && i == 0) *fwd_seq += 1u;  // epoch base of this forward's one-shot all-reduces (tensor parallel target)
 }
 
 // ----------------------------------------------------------------------------------
@@ -100,24 +101,24 @@ __global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __r
 //   residual_out = bf16(r)
 //   y          = bf16(r * rsqrt(mean(r^2) + eps) * w)        (layers/layernorm.py:64-88, compiled form)
 // ----------------------------------------------------------------------------------
-// One-shot all-reduce input (tensor parallel): every rank's bf16 contribution sits in THIS rank's symmetric
-// buffer (pushed there by ar_publish_kernel over NVLink); flags[r] holds the last epoch rank r has published.
+// One-shot, low-latency ("LL") all-reduce input (tensor parallel).  Every rank's bf16 contribution sits in THIS
+// rank's symmetric buffer as 8-byte words {2 x bf16, flag}: ar_publish_kernel pushes them over NVLink with plain
+// vector stores (an aligned 8-byte store is atomic, so data and flag become visible together — no fence, no separate
+// signal), and the consumer simply re-reads a word until its flag equals the expected epoch.  The epoch is
+// (target-forward sequence number) * 512 + (static index of the all-reduce inside the forward) + 1, so it needs no
+// cross-kernel bookkeeping and a static CUDA graph can replay it.  Slots are double-buffered by call parity; a rank
+// cannot run two all-reduces ahead of a peer because it needs that peer's words of the previous one first.
 struct SymmIn {
-  const uint8_t* base;    // this rank's symmetric buffer; nullptr = not used
-  const unsigned* epoch;  // local: epoch of the all-reduce to consume (written by the local ar_publish_kernel)
+  const uint8_t* base;      // this rank's symmetric buffer; nullptr = not used
+  const unsigned* fwd_seq;  // local: sequence number of the current target forward
+  int call_idx;             // static index of this all-reduce inside the forward
   int n_ranks;
   unsigned slot_bytes;
 };
-constexpr int kSymmFlagsBytes = 1024;  // 8 flags, one per 128-byte line
 constexpr int kSymmMaxRanks = 8;
-
-SSDK_DEVINL unsigned ld_acquire_sys_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-SSDK_DEVINL void st_release_sys_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+SSDK_DEVINL unsigned symm_epoch(const unsigned* fwd_seq, int call_idx) { return __ldcg(fwd_seq) * 512u + (unsigned)call_idx + 1u; }
+SSDK_DEVINL size_t symm_slot_off(int call_idx, int rank, unsigned slot_bytes) {
+  return ((size_t)(call_idx & 1) * kSymmMaxRanks + rank) * slot_bytes;
 }
 
 struct NormParams {
@@ -143,19 +144,12 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
   if (threadIdx.x == 0) trace_mark(TR_NORM);
   const int m = blockIdx.x;
   const int d = p.d;
-  // ---- one-shot all-reduce input: wait until every rank has pushed its contribution of this epoch ----
+  // ---- one-shot all-reduce input: words carry their own flag, nothing to wait for up front ----
   const uint8_t* symm_slots = nullptr;
+  unsigned symm_e = 0;
   if (p.symm.base) {
-    const unsigned e = __ldcg(p.symm.epoch);
-    if (threadIdx.x < p.symm.n_ranks) {
-      const unsigned* flag = reinterpret_cast<const unsigned*>(p.symm.base + threadIdx.x * 128);
-      const long long t0 = clock64();
-      while ((int)(ld_acquire_sys_u32(flag) - e) < 0) {
-        if (clock64() - t0 > 8000000000LL) __trap();
-      }
-    }
-    __syncthreads();
-    symm_slots = p.symm.base + kSymmFlagsBytes + (size_t)(e & 1u) * kSymmMaxRanks * p.symm.slot_bytes;
+    symm_e = symm_epoch(p.symm.fwd_seq, p.symm.call_idx);
+    symm_slots = p.symm.base + symm_slot_off(p.symm.call_idx, 0, p.symm.slot_bytes);
   }
   const __nv_bfloat16* erow = nullptr;
   bool zero_row = false;
@@ -168,21 +162,37 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
   for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
     float x[8];
     if (symm_slots) {
-      // sum the ranks' bf16 contributions in rank order (identical on every rank), fp32 accumulate, one bf16 rounding
-      uint4 v[kSymmMaxRanks];
-#pragma unroll
-      for (int r = 0; r < kSymmMaxRanks; ++r)
-        if (r < p.symm.n_ranks)
-          v[r] = __ldcg(reinterpret_cast<const uint4*>(symm_slots + (size_t)r * p.symm.slot_bytes) + ((size_t)m * d + i) / 8);
+      // sum the ranks' bf16 contributions in rank order (identical on every rank), fp32 accumulate, one bf16 rounding.
+      // 8 elements = 4 words {2 x bf16, flag} = two 16-byte loads per rank; spin until all four flags show this epoch.
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = 0.f;
+      const size_t word0 = ((size_t)m * d + i) / 2;
+      uint4 lo[kSymmMaxRanks], hi[kSymmMaxRanks];
+      const long long t0 = clock64();
+      bool ready = false;
+      while (!ready) {
+        ready = true;
+#pragma unroll
+        for (int r = 0; r < kSymmMaxRanks; ++r) {
+          if (r < p.symm.n_ranks) {
+            const uint4* src = reinterpret_cast<const uint4*>(symm_slots + (size_t)r * p.symm.slot_bytes) + word0 / 2;
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo[r].x), "=r"(lo[r].y), "=r"(lo[r].z), "=r"(lo[r].w) : "l"(src));
+            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi[r].x), "=r"(hi[r].y), "=r"(hi[r].z), "=r"(hi[r].w) : "l"(src + 1));
+            ready = ready && lo[r].y == symm_e && lo[r].w == symm_e && hi[r].y == symm_e && hi[r].w == symm_e;
+          }
+        }
+        if (!ready && clock64() - t0 > 8000000000LL) __trap();
+      }
 #pragma unroll
       for (int r = 0; r < kSymmMaxRanks; ++r) {
         if (r < p.symm.n_ranks) {
-          float c[8];
-          unpack_bf16x8(v[r], c);
+          const uint32_t w4[4] = {lo[r].x, lo[r].z, hi[r].x, hi[r].z};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] += c[j];
+          for (int q = 0; q < 4; ++q) {
+            const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+            x[2 * q] += c.x;
+            x[2 * q + 1] += c.y;
+          }
         }
       }
 #pragma unroll
@@ -227,11 +237,9 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
 // ar_publish_kernel — first half of the one-shot all-reduce that replaces dist.all_reduce on the row-parallel
 // boundaries (layers/linear.py:195-199, embed_head.py:56).  Each rank reduces its split-K partials (or gathers its
 // masked embedding rows), rounds to bf16 exactly like the reference's per-rank F.linear output, and PUSHES the
-// result over NVLink into slot[parity][my_rank] of EVERY rank's symmetric buffer; the last CTA then releases
-// flag[my_rank] = epoch on every rank (st.release.sys).  The consumer (add_rmsnorm_kernel with SymmIn) acquires the
-// flags, sums the slots in rank order and continues with residual add + RMSNorm — no NCCL call, no extra pass.
-// Slots are double-buffered by epoch parity; a rank cannot run two epochs ahead of a peer because it needs that
-// peer's flag of the previous epoch first.
+// result as {2 x bf16, epoch} words over NVLink into slot[call parity][my_rank] of EVERY rank's symmetric buffer.
+// The consumer (add_rmsnorm_kernel with SymmIn) spins on the words themselves, sums the ranks in rank order and
+// continues with residual add + RMSNorm — no NCCL call, no fence, no extra pass over the data.
 // ----------------------------------------------------------------------------------
 struct ArPublishParams {
   GemmOut x;
@@ -242,17 +250,16 @@ struct ArPublishParams {
   int M, d, n_ranks, rank;
   uint8_t* peer[kSymmMaxRanks];
   unsigned slot_bytes;
-  unsigned* epoch;   // local: last published epoch
-  unsigned* ticket;  // local, zero on entry/exit
+  const unsigned* fwd_seq;
+  int call_idx;
 };
 
 __global__ void __launch_bounds__(256) ar_publish_kernel(ArPublishParams p) {
-  __shared__ bool is_last;
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(TR_MISC);
-  const unsigned e = __ldcg(p.epoch) + 1u;
-  const size_t slot_off = kSymmFlagsBytes + ((size_t)(e & 1u) * kSymmMaxRanks + p.rank) * p.slot_bytes;
+  const unsigned e = symm_epoch(p.fwd_seq, p.call_idx);
+  const size_t slot_off = symm_slot_off(p.call_idx, p.rank, p.slot_bytes);
   const int total = p.M * p.d;
   for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 8; idx < total; idx += gridDim.x * blockDim.x * 8) {
     const int m = idx / p.d, i = idx - m * p.d;
@@ -269,22 +276,15 @@ __global__ void __launch_bounds__(256) ar_publish_kernel(ArPublishParams p) {
       gemm_out_at8(p.x, m, i, x);
     }
     const uint4 v = pack_bf16x8(x);
+    const uint4 lo = make_uint4(v.x, e, v.y, e), hi = make_uint4(v.z, e, v.w, e);
 #pragma unroll
-    for (int r = 0; r < kSymmMaxRanks; ++r)
-      if (r < p.n_ranks) *(reinterpret_cast<uint4*>(p.peer[r] + slot_off) + idx / 8) = v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned tk = atomicAdd(p.ticket, 1u);
-    is_last = (tk == gridDim.x - 1u);
-  }
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    *p.ticket = 0u;
-    __threadfence_system();
-    for (int r = 0; r < p.n_ranks; ++r) st_release_sys_u32(reinterpret_cast<unsigned*>(p.peer[r] + p.rank * 128), e);
-    *p.epoch = e;
+    for (int r = 0; r < kSymmMaxRanks; ++r) {
+      if (r < p.n_ranks) {
+        uint4* dst = reinterpret_cast<uint4*>(p.peer[r] + slot_off) + idx / 4;
+        dst[0] = lo;
+        dst[1] = hi;
+      }
+    }
   }
 }
 

@@ -471,16 +471,18 @@ static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w
 
 // y = allreduce_sum(bf16(sum_s partials)) for tensor-parallel row-parallel linears
 // (layers/linear.py:195-199): reduce split-K locally, round to bf16 like F.linear, NCCL bf16 sum.
-static SymmIn symm_in(ssdk_engine* e) {
+static SymmIn symm_in(ssdk_engine* e, int call_idx) {
   SymmIn s;
   s.base = e->symm_peer[e->model[SSDK_TARGET].cfg.tp_rank];
-  s.epoch = e->ws.ar_state;
+  s.fwd_seq = e->ws.ar_state;
+  s.call_idx = call_idx;
   s.n_ranks = e->symm_n;
   s.slot_bytes = e->symm_slot_bytes;
   return s;
 }
 // first half of the one-shot all-reduce: reduce split-K locally, push bf16 to every rank, release flags
-static int enqueue_ar_publish(ssdk_engine* e, Launcher& L, const GemmOut* x, const NormParams* embed_src, int M, int d) {
+static int enqueue_ar_publish(ssdk_engine* e, Launcher& L, const GemmOut* x, const NormParams* embed_src, int M, int d,
+                              int call_idx) {
   Model& m = e->model[SSDK_TARGET];
   ArPublishParams ap;
   memset(&ap, 0, sizeof(ap));
@@ -492,7 +494,7 @@ static int enqueue_ar_publish(ssdk_engine* e, Launcher& L, const GemmOut* x, con
   ap.M = M; ap.d = d; ap.n_ranks = e->symm_n; ap.rank = m.cfg.tp_rank;
   for (int r = 0; r < e->symm_n; ++r) ap.peer[r] = e->symm_peer[r];
   ap.slot_bytes = e->symm_slot_bytes;
-  ap.epoch = e->ws.ar_state; ap.ticket = e->ws.ar_state + 1;
+  ap.fwd_seq = e->ws.ar_state; ap.call_idx = call_idx;
   const int n8 = M * d / 8;
   return L.go(ar_publish_kernel, dim3(std::max(1, std::min((n8 + 255) / 256, num_sms()))), dim3(256), 0, ap);
 }
@@ -533,7 +535,8 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
   const int64_t cache_layer_stride = m.num_blocks * bs * m.KV * m.hd;
 
   CKI(L.go(prep_kernel, dim3(1), dim3(kMaxTokens), 0, f.ctx0, f.block_tables, mb, bs, f.B, f.Q, f.pos_offset,
-           w.positions, w.slot_mapping, w.context_lens));
+           w.positions, w.slot_mapping, w.context_lens,
+           (f.which == SSDK_TARGET && tp > 1 && e->symm_n == tp) ? w.ar_state : (unsigned*)nullptr));
 
   int TQ, MT, nqt, nsplit;
   CKI(attn_plan(m, f.B, f.Q, &TQ, &MT, &nqt, &nsplit, e->max_ctx_hint));
@@ -541,6 +544,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
 
   const bool use_symm = tp > 1 && e->symm_n == tp;
   bool prev_symm = false;
+  int ar_idx = 0, prev_idx = 0;  // static index of each one-shot all-reduce inside this forward (epoch = seq*512+idx+1)
   GemmOut prev;  // output of the previous row-parallel GEMM feeding the next norm
   prev.dense = nullptr; prev.partial = nullptr; prev.S = 0; prev.M = M; prev.N = m.d;
 
@@ -561,8 +565,8 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
         ep.ids = f.ids; ep.ids_stride = f.ids_stride; ep.embed = m.embed.ptr;
         ep.vocab_start = m.cfg.tp_rank * m.vocab_local; ep.vocab_rows = m.vocab_local;
         if (use_symm) {
-          CKI(enqueue_ar_publish(e, L, nullptr, &ep, M, m.d));
-          np.symm = symm_in(e);
+          CKI(enqueue_ar_publish(e, L, nullptr, &ep, M, m.d, ar_idx));
+          np.symm = symm_in(e, ar_idx++);
         } else {
           ep.eps = m.cfg.rms_eps; ep.d = m.d; ep.residual_out = w.dense_tmp;  // y = null: gather only
           CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, ep));
@@ -573,7 +577,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
       }
     } else {
       np.x = prev;
-      if (prev_symm) np.symm = symm_in(e);
+      if (prev_symm) np.symm = symm_in(e, prev_idx);
       np.residual_in = w.residual;
     }
     CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, np));
@@ -602,9 +606,11 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     GemmOut oproj;
     oproj.dense = nullptr; oproj.partial = w.partials; oproj.S = S; oproj.M = M; oproj.N = m.d;
     bool oproj_symm = false;
+    int oproj_idx = 0;
     if (tp > 1) {
       if (use_symm) {
-        CKI(enqueue_ar_publish(e, L, &oproj, nullptr, M, m.d));
+        CKI(enqueue_ar_publish(e, L, &oproj, nullptr, M, m.d, ar_idx));
+        oproj_idx = ar_idx++;
         oproj_symm = true;
       } else {
         CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &oproj));
@@ -615,7 +621,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     NormParams pn;
     memset(&pn, 0, sizeof(pn));
     pn.x = oproj; pn.residual_in = w.residual; pn.w = lw.post_norm; pn.eps = m.cfg.rms_eps;
-    if (oproj_symm) pn.symm = symm_in(e);
+    if (oproj_symm) pn.symm = symm_in(e, oproj_idx);
     pn.y = w.hidden; pn.residual_out = w.residual; pn.d = m.d;
     CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, pn));
 
@@ -633,7 +639,8 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     prev.dense = nullptr; prev.partial = w.partials; prev.S = S; prev.M = M; prev.N = m.d;
     if (tp > 1) {
       if (use_symm) {
-        CKI(enqueue_ar_publish(e, L, &prev, nullptr, M, m.d));
+        CKI(enqueue_ar_publish(e, L, &prev, nullptr, M, m.d, ar_idx));
+        prev_idx = ar_idx++;
         prev_symm = true;
       } else {
         CKI(enqueue_tp_allreduce(e, L, S, M, m.d, &prev));
@@ -644,7 +651,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
   NormParams fn;
   memset(&fn, 0, sizeof(fn));
   fn.x = prev; fn.residual_in = w.residual; fn.w = m.final_norm; fn.eps = m.cfg.rms_eps; fn.y = w.hidden;
-  if (prev_symm) fn.symm = symm_in(e);
+  if (prev_symm) fn.symm = symm_in(e, prev_idx);
   fn.residual_out = nullptr; fn.d = m.d;
   CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, fn));
 
@@ -1010,8 +1017,8 @@ int64_t ssdk_symm_bytes(ssdk_handle h) {
   if (!h) return fail("null handle");
   const Model& m = h->model[SSDK_TARGET];
   if (m.cfg.tp_size <= 1) return 0;
-  const int64_t slot = (int64_t)kMaxTokens * m.d * 2;
-  return kSymmFlagsBytes + 2 * kSymmMaxRanks * slot;
+  const int64_t slot = (int64_t)kMaxTokens * m.d * 4;  // {2 x bf16, flag} words
+  return 2 * kSymmMaxRanks * slot;
 }
 int ssdk_bind_symm(ssdk_handle h, void* const* peer_ptrs, int n_peers) {
   if (!h || !peer_ptrs) return fail("bind_symm: null argument");
@@ -1022,7 +1029,7 @@ int ssdk_bind_symm(ssdk_handle h, void* const* peer_ptrs, int n_peers) {
     h->symm_peer[r] = (uint8_t*)peer_ptrs[r];
   }
   h->symm_n = n_peers;
-  h->symm_slot_bytes = (unsigned)((size_t)kMaxTokens * m.d * 2);
+  h->symm_slot_bytes = (unsigned)((size_t)kMaxTokens * m.d * 4);
   return 0;
 }
 
