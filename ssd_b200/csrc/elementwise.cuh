@@ -68,6 +68,37 @@ SSDK_DEVINL void gemm_out_at8(const GemmOut& g, int m, int n, float* f) {
   for (int i = 0; i < 8; ++i) f[i] = bf16_round(f[i]);
 }
 
+// two 2-column groups (cols a, a+1 and b, b+1; a, b even) with every load of a batch in flight together
+SSDK_DEVINL void gemm_out_at2x2(const GemmOut& g, int m, int a, int b, float* fa, float* fb) {
+  if (g.S == 0) {
+    const float2 va = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g.dense + (size_t)m * g.N + a));
+    const float2 vb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g.dense + (size_t)m * g.N + b));
+    fa[0] = va.x; fa[1] = va.y; fb[0] = vb.x; fb[1] = vb.y;
+    return;
+  }
+  fa[0] = fa[1] = fb[0] = fb[1] = 0.f;
+  const float* base = g.partial + (size_t)m * g.N;
+  const size_t stride = (size_t)g.M * g.N;
+  for (int s0 = 0; s0 < g.S; s0 += 8) {
+    float2 va[8], vb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (s0 + u < g.S) {
+        va[u] = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(s0 + u) * stride + a));
+        vb[u] = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(s0 + u) * stride + b));
+      } else {
+        va[u] = make_float2(0.f, 0.f);
+        vb[u] = va[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      fa[0] += va[u].x; fa[1] += va[u].y; fb[0] += vb[u].x; fb[1] += vb[u].y;
+    }
+  }
+  fa[0] = bf16_round(fa[0]); fa[1] = bf16_round(fa[1]); fb[0] = bf16_round(fb[0]); fb[1] = bf16_round(fb[1]);
+}
+
 // ----------------------------------------------------------------------------------
 // prep: positions / slot_mapping / context_lens for one forward of `batch` sequences
 // with q_len tokens each, token j of sequence b at position ctx0[b] + pos_offset + j.
@@ -136,8 +167,11 @@ struct NormParams {
   int d;
 };
 
-__global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
-  extern __shared__ float rbuf[];  // d floats
+// blockDim.x = d/16..d/8 (<= 512): every thread owns at most TWO 8-element slices that stay in registers between the passes,
+// and all of its loads (weights, residual, GEMM partials / all-reduce words) are in flight together — the kernel costs
+// ~2 L2 round trips + one block reduction.  Rows wider than 8192 fall back to a shared-memory staged loop.
+__global__ void __launch_bounds__(512) add_rmsnorm_kernel(NormParams p) {
+  extern __shared__ float rbuf[];  // d floats (only used when d > 8 * blockDim.x)
   __shared__ float red[32];
   pdl_launch_dependents();
   pdl_wait();
@@ -159,7 +193,17 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
     else erow = p.embed + (size_t)id * d;
   }
   float ss = 0.f;
-  for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
+  const bool single = (int)blockDim.x * 16 >= d;  // <= 2 slices per thread: keep them in registers
+  float xreg[2][8], wreg[2][8];
+  if (single && p.y) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = (c * blockDim.x + threadIdx.x) * 8;
+      if (i < d) unpack_bf16x8(*reinterpret_cast<const uint4*>(p.w + i), wreg[c]);
+    }
+  }
+  int chunk = 0;
+  for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8, ++chunk) {
     float x[8];
     if (symm_slots) {
       // sum the ranks' bf16 contributions in rank order (identical on every rank), fp32 accumulate, one bf16 rounding.
@@ -216,19 +260,37 @@ __global__ void __launch_bounds__(256) add_rmsnorm_kernel(NormParams p) {
     if (p.residual_out) *reinterpret_cast<uint4*>(p.residual_out + (size_t)m * d + i) = pack_bf16x8(x);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      rbuf[i + j] = x[j];
+      if (single) {
+        if (chunk == 0) xreg[0][j] = x[j];
+        else xreg[1][j] = x[j];
+      } else {
+        rbuf[i + j] = x[j];
+      }
       ss += x[j] * x[j];
     }
   }
   ss = block_sum(ss, red);
   const float rstd = rsqrtf(ss / (float)d + p.eps);
   if (p.y) {
-    for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
-      float w[8], o[8];
-      unpack_bf16x8(*reinterpret_cast<const uint4*>(p.w + i), w);
+    if (single) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = rbuf[i + j] * rstd * w[j];
-      *reinterpret_cast<uint4*>(p.y + (size_t)m * d + i) = pack_bf16x8(o);
+      for (int c = 0; c < 2; ++c) {
+        const int i = (c * blockDim.x + threadIdx.x) * 8;
+        if (i < d) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = xreg[c][j] * rstd * wreg[c][j];
+          *reinterpret_cast<uint4*>(p.y + (size_t)m * d + i) = pack_bf16x8(o);
+        }
+      }
+    } else {
+      for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
+        float w[8], o[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(p.w + i), w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rbuf[i + j] * rstd * w[j];
+        *reinterpret_cast<uint4*>(p.y + (size_t)m * d + i) = pack_bf16x8(o);
+      }
     }
   }
 }
@@ -326,28 +388,35 @@ __global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
   if (kind == 2) {
     if (slot < 0) return;
     __nv_bfloat16* dst = p.v_cache + ((size_t)slot * KV + (head - H - KV)) * hd;
-    for (int i = lane; i < hd; i += 32) dst[i] = f2bf(gemm_out_at(p.qkv, m, col0 + i));
+    for (int i = 2 * lane; i < half; i += 64) {  // same (i, i + half) split as q/k: all loads of a lane in flight
+      float a[2], b[2];
+      gemm_out_at2x2(p.qkv, m, col0 + i, col0 + half + i, a, b);
+      *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(a[0], a[1]);
+      *reinterpret_cast<__nv_bfloat162*>(dst + half + i) = __floats2bfloat162_rn(b[0], b[1]);
+    }
     return;
   }
   if (kind == 1 && slot < 0) return;
 
-  // each lane owns pairs (i, i + half), i = lane, lane+32, ...   (hd <= 256)
-  float x1[4], x2[4];
-  int np = 0;
+  // each lane owns the element pairs (i, i+1) and (i + half, i + half + 1), i = 2*lane (+64 for hd = 256)
+  float x1[2][2], x2[2][2];
   float ss = 0.f;
-  for (int i = lane; i < half; i += 32, ++np) {
-    x1[np] = gemm_out_at(p.qkv, m, col0 + i);
-    x2[np] = gemm_out_at(p.qkv, m, col0 + half + i);
-    ss += x1[np] * x1[np] + x2[np] * x2[np];
+  int np = 0;
+  for (int i = 2 * lane; i < half; i += 64, ++np) {
+    gemm_out_at2x2(p.qkv, m, col0 + i, col0 + half + i, x1[np], x2[np]);
+    ss += x1[np][0] * x1[np][0] + x1[np][1] * x1[np][1] + x2[np][0] * x2[np][0] + x2[np][1] * x2[np][1];
   }
   const __nv_bfloat16* nw = (kind == 0) ? p.q_norm_w : p.k_norm_w;
   if (nw) {
     ss = warp_sum(ss);
     const float rstd = rsqrtf(ss / (float)hd + p.norm_eps);
     int t = 0;
-    for (int i = lane; i < half; i += 32, ++t) {
-      x1[t] = bf16_round(x1[t] * rstd * bf2f(nw[i]));
-      x2[t] = bf16_round(x2[t] * rstd * bf2f(nw[half + i]));
+    for (int i = 2 * lane; i < half; i += 64, ++t) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        x1[t][e] = bf16_round(x1[t][e] * rstd * bf2f(nw[i + e]));
+        x2[t][e] = bf16_round(x2[t][e] * rstd * bf2f(nw[half + i + e]));
+      }
     }
   }
   const long long pos = p.positions[m];
@@ -355,10 +424,12 @@ __global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
   __nv_bfloat16* dst = (kind == 0) ? p.q_out + (size_t)m * H * hd + (size_t)head * hd
                                    : p.k_cache + ((size_t)slot * KV + (head - H)) * hd;
   int t = 0;
-  for (int i = lane; i < half; i += 32, ++t) {
-    const float c = cs[i], s = cs[half + i];
-    dst[i] = f2bf(x1[t] * c - x2[t] * s);
-    dst[half + i] = f2bf(x2[t] * c + x1[t] * s);
+  for (int i = 2 * lane; i < half; i += 64, ++t) {
+    const float2 c = *reinterpret_cast<const float2*>(cs + i), sn = *reinterpret_cast<const float2*>(cs + half + i);
+    *reinterpret_cast<__nv_bfloat162*>(dst + i) =
+        __floats2bfloat162_rn(x1[t][0] * c.x - x2[t][0] * sn.x, x1[t][1] * c.y - x2[t][1] * sn.y);
+    *reinterpret_cast<__nv_bfloat162*>(dst + half + i) =
+        __floats2bfloat162_rn(x2[t][0] * c.x + x1[t][0] * sn.x, x2[t][1] * c.y + x1[t][1] * sn.y);
   }
 }
 

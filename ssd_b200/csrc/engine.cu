@@ -128,6 +128,9 @@ static int num_sms() {
   }
   return g_num_sms;
 }
+// add_rmsnorm_kernel geometry: <= 2 register-resident 8-element slices per thread (512 threads), smem staging beyond
+static int norm_threads(int d) { return std::max(32, std::min(512, ((d / 8 + 31) / 32) * 32)); }
+static size_t norm_smem(int d) { return d > 8192 ? (size_t)d * 4 : 0; }
 static int umma_n_for(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : 64); }
 
 static int auto_splits(int tiles, int num_kb) {
@@ -569,7 +572,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
           np.symm = symm_in(e, ar_idx++);
         } else {
           ep.eps = m.cfg.rms_eps; ep.d = m.d; ep.residual_out = w.dense_tmp;  // y = null: gather only
-          CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, ep));
+          CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), ep));
           CKN(ncclAllReduce(w.dense_tmp, w.dense_tmp, (size_t)M * m.d, ncclBfloat16, ncclSum, e->comm, L.st));
           L.barrier_op();
           np.x.dense = w.dense_tmp; np.x.S = 0; np.x.M = M; np.x.N = m.d;
@@ -580,7 +583,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
       if (prev_symm) np.symm = symm_in(e, prev_idx);
       np.residual_in = w.residual;
     }
-    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, np));
+    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), np));
 
     // ---- QKV projection -> RoPE (+qk norm) -> KV store ----
     int S = 1;
@@ -623,7 +626,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     pn.x = oproj; pn.residual_in = w.residual; pn.w = lw.post_norm; pn.eps = m.cfg.rms_eps;
     if (oproj_symm) pn.symm = symm_in(e, oproj_idx);
     pn.y = w.hidden; pn.residual_out = w.residual; pn.d = m.d;
-    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, pn));
+    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), pn));
 
     // ---- MLP: gate|up with fused SiLU*mul when the tile count fills the machine ----
     const int silu_tiles = (m.ffn + 63) / 64;
@@ -653,7 +656,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
   fn.x = prev; fn.residual_in = w.residual; fn.w = m.final_norm; fn.eps = m.cfg.rms_eps; fn.y = w.hidden;
   if (prev_symm) fn.symm = symm_in(e, prev_idx);
   fn.residual_out = nullptr; fn.d = m.d;
-  CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)m.d * 4, fn));
+  CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), fn));
 
   // ---- lm_head ----
   if (f.logits_mode != 0) {
@@ -1283,7 +1286,7 @@ int ssdk_rmsnorm(const void* x, const void* residual_in, const void* w, float ep
   np.x.dense = (const bf16*)x; np.x.S = 0; np.x.M = M; np.x.N = d;
   np.residual_in = (const bf16*)residual_in; np.w = (const bf16*)w; np.eps = eps;
   np.y = (bf16*)y; np.residual_out = (bf16*)residual_out; np.d = d;
-  return L.go(add_rmsnorm_kernel, dim3(M), dim3(256), (size_t)d * 4, np);
+  return L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(d)), norm_smem(d), np);
 }
 
 int ssdk_rope_store_kv(const void* qkv, const int64_t* positions, const int32_t* slot_mapping, const float* rope_table,
