@@ -193,6 +193,12 @@ def run_ours(args):
                "accept_len": sum(lens) / max(1, len(lens))}
 
     if rank != 0:
+        if world > 1:
+            try:
+                dist.barrier()
+                dist.destroy_process_group()
+            except Exception:
+                pass
         return
     # ---------------- roofline ----------------
     peak, peak_src = measured_peaks()
@@ -216,6 +222,12 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
     }
     print(json.dumps(out), flush=True)
+    if world > 1:
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def gemm_roofline(runner, peak):
@@ -241,8 +253,17 @@ def gemm_roofline(runner, peak):
     ms = sum(ts) / len(ts)
     nbytes = w.numel() * 2
     ach = nbytes / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": f"gemm_ws_kernel<16,EPI_SILU> gate|up [{w.shape[0]}x{w.shape[1]}] M={M}",
-            "achieved": ach, "unit": "GB/s", "frac": ach / peak, "traffic": None, "launch_ms": ms, "bytes_per_launch": nbytes}
+    name = f"gemm_ws_kernel<16,EPI_SILU> gate|up [{w.shape[0]}x{w.shape[1]}] M={M}"
+    traffic = None  # dram__bytes_read+write of the same launch from the committed ncu --set full capture, if it matches
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            t = json.load(f)
+        if t["kernel"] == name:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": name, "achieved": ach, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+            "launch_ms": ms, "bytes_per_launch": nbytes}
 
 
 # ---------------------------------------------------------------------------------------- CPU baseline
