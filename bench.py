@@ -119,7 +119,8 @@ def run_ours(args):
     tshape, dshape, desc = WORKLOADS[args.workload]
     K = args.spec_k
     root = tempfile.mkdtemp(prefix="ssd_b200_bench_")
-    max_len = 4096
+    need = args.prompt_len + (args.steps + max(args.warmup, 3) + 6) * (K + 1) + 64
+    max_len = max(4096, -(-need // 256) * 256)
     tdir = synth.make_model_dir(root, tshape, "target", seed=0, alpha=args.alpha)
     ddir = synth.make_model_dir(root, dshape, "draft", seed=0, alpha=args.alpha)
     t_init = time.time()
@@ -208,7 +209,8 @@ def run_ours(args):
     step_frac = (bstep / (ms_dev / steps * 1e-3) / 1e9 / peak) if bstep else None
     if roof is not None:
         roof.update({"peak": peak, "peak_source": peak_src, "step_bytes": bstep, "step_frac": step_frac})
-    cpu = cpu_baseline(tshape, dshape, K, args.alpha, sample_steps=3) if not args.no_cpu else None
+    # the CPU baseline is measured on rank 0 at N=1 only (host cores are shared by the ranks otherwise)
+    cpu = cpu_baseline(tshape, dshape, K, args.alpha, sample_steps=3) if (not args.no_cpu and world == 1) else None
     out = {
         "metric": "decode tokens/sec (sync speculative decoding, accept-len reported)", "value": toks_dev / (ms_dev * 1e-3),
         "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_dev / steps,

@@ -34,7 +34,6 @@ struct AttnParams {
   __nv_bfloat16* out;            // [B*Q, H*hd]
   float* part_o;                 // [B*Q*H, n_split, hd]
   float* part_lse;               // [B*Q*H, n_split]
-  unsigned* counters;            // [B*n_qtiles*KV] arrival tickets (zero on entry, zero again on exit)
   int B, Q, H, KV, block_size, max_blocks, n_split, TQ, n_qtiles;
   float scale_log2;              // softmax scale * log2(e)
 };

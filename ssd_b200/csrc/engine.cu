@@ -437,7 +437,8 @@ static int enqueue_attention(Launcher& L, const bf16* q, const bf16* kc, const b
                              int nsplit) {
   AttnParams a;
   a.q = q; a.k_cache = kc; a.v_cache = vc; a.block_tables = bt; a.context_lens = ctx_lens; a.out = out;
-  a.part_o = part_o; a.part_lse = part_lse; a.counters = counters;
+  a.part_o = part_o; a.part_lse = part_lse;
+  (void)counters;
   a.B = B; a.Q = Q; a.H = H; a.KV = KV; a.block_size = block_size; a.max_blocks = max_blocks;
   a.n_split = nsplit; a.TQ = TQ; a.n_qtiles = nqt;
   a.scale_log2 = scale * 1.4426950408889634f;
