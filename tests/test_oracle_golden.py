@@ -123,3 +123,30 @@ def test_sync_sd_trace_matches_reference(family):
         decisions += B * (K + 1) + sum(nacc)
         s.advance(nacc, nxt)
     assert soft_total <= max(2, decisions // 20), f"{soft_total} near-tie flips in {decisions} decisions"
+
+
+def test_baseline_config0_plumbing_1b_shapes_on_cpu():
+    """BASELINE.json configs[0] — 'Llama-3 1B AR greedy b=1 on CPU (plumbing, no GPU)': the reference itself cannot
+    run on CPU (engine/model_runner.py:88-89 hard-require CUDA), so the plumbing check is the oracle driving the
+    Llama-3.2-1B layer shapes (2 of 16 layers, reduced vocab to keep the CPU suite fast) autoregressively and being
+    reproduced exactly by its own speculative path (SD == AR)."""
+    from oracle.model import ModelCfg, random_weights
+    cfg = ModelCfg(hidden=2048, layers=2, heads=32, kv_heads=8, head_dim=64, ffn=8192, vocab=4096, max_pos=512)
+    w = random_weights(cfg, 3)
+    mb, bs = 1, 256
+    ar = SpecSession(OracleModel(cfg, w, mb, bs), None, 0, mb)
+    bt = contiguous_block_tables(1, mb)
+    prompt = list(range(7, 39))
+    ar.prefill([prompt], [0.0], bt, None)
+    ar_tokens = []
+    for _ in range(12):
+        ar_tokens += ar.ar_step()
+    K = 3
+    sd = SpecSession(OracleModel(cfg, w, mb, bs), OracleModel(cfg, w, mb, bs), K, mb)
+    sd.prefill([prompt], [0.0], bt, bt.clone())
+    sd_tokens = []
+    while len(sd_tokens) < 12:
+        suf, *_ = sd.spec_step()
+        assert len(suf[0]) == K + 1  # identical draft: everything is accepted
+        sd_tokens += suf[0]
+    assert sd_tokens[:12] == ar_tokens[:12]
