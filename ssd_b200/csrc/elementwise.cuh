@@ -142,6 +142,7 @@ __global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __r
 struct SymmIn {
   const uint8_t* base;      // this rank's symmetric buffer; nullptr = not used
   const unsigned* fwd_seq;  // local: sequence number of the current target forward
+  int no_dep_wait;          // 1: the consumer may skip griddepcontrol.wait (see add_rmsnorm_kernel)
   int call_idx;             // static index of this all-reduce inside the forward
   int n_ranks;
   unsigned slot_bytes;
@@ -174,7 +175,12 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(NormParams p) {
   extern __shared__ float rbuf[];  // d floats (only used when d > 8 * blockDim.x)
   __shared__ float red[32];
   pdl_launch_dependents();
-  pdl_wait();
+  // All-reduce consumers after a row-parallel GEMM are pure dataflow: every input word (including THIS rank's own
+  // contribution) carries the epoch flag, so the kernel does not have to wait for the publishing kernel to *complete*
+  // (which would include the acknowledgement of its remote NVLink stores, ~4 us at TP=8) — it can start polling as soon
+  // as it is resident.  Seeing this rank's own flagged words implies the local chain up to the publish has run, which is
+  // what protects `hidden` / `residual` (read by earlier kernels of the chain) from being overwritten too early.
+  if (!(p.symm.base && p.symm.no_dep_wait)) pdl_wait();
   if (threadIdx.x == 0) trace_mark(TR_NORM);
   const int m = blockIdx.x;
   const int d = p.d;

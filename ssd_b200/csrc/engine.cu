@@ -478,8 +478,9 @@ static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w
 
 // y = allreduce_sum(bf16(sum_s partials)) for tensor-parallel row-parallel linears
 // (layers/linear.py:195-199): reduce split-K locally, round to bf16 like F.linear, NCCL bf16 sum.
-static SymmIn symm_in(ssdk_engine* e, int call_idx) {
+static SymmIn symm_in(ssdk_engine* e, int call_idx, bool no_dep_wait = false) {
   SymmIn s;
+  s.no_dep_wait = no_dep_wait ? 1 : 0;
   s.base = e->symm_peer[e->model[SSDK_TARGET].cfg.tp_rank];
   s.fwd_seq = e->ws.ar_state;
   s.call_idx = call_idx;
@@ -584,7 +585,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
       }
     } else {
       np.x = prev;
-      if (prev_symm) np.symm = symm_in(e, prev_idx);
+      if (prev_symm) np.symm = symm_in(e, prev_idx, true);
       np.residual_in = w.residual;
     }
     CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), np));
@@ -628,7 +629,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     NormParams pn;
     memset(&pn, 0, sizeof(pn));
     pn.x = oproj; pn.residual_in = w.residual; pn.w = lw.post_norm; pn.eps = m.cfg.rms_eps;
-    if (oproj_symm) pn.symm = symm_in(e, oproj_idx);
+    if (oproj_symm) pn.symm = symm_in(e, oproj_idx, true);
     pn.y = w.hidden; pn.residual_out = w.residual; pn.d = m.d;
     CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), pn));
 
@@ -658,7 +659,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
   NormParams fn;
   memset(&fn, 0, sizeof(fn));
   fn.x = prev; fn.residual_in = w.residual; fn.w = m.final_norm; fn.eps = m.cfg.rms_eps; fn.y = w.hidden;
-  if (prev_symm) fn.symm = symm_in(e, prev_idx);
+  if (prev_symm) fn.symm = symm_in(e, prev_idx, true);
   fn.residual_out = nullptr; fn.d = m.d;
   CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), fn));
 
