@@ -181,6 +181,59 @@ def gen_verify_ratio(ssd):
     print("verify_ratio ok")
 
 
+def gen_verify_mixed(ssd):
+    """Per-row temperatures (greedy and sampled rows in one batch), cache-hit gating without jit, K at both ends of the
+    supported range: pins the row-selection logic of verify.py:57-62,127,146,167."""
+    import ssd.utils.verify as vmod
+
+    g = torch.Generator().manual_seed(15)
+    cases = {}
+    real_rand_like, real_multinomial = torch.rand_like, torch.multinomial
+    cfgs = [
+        (4, 6, 384, [0.0, 0.7, 1.0, 0.0], [0.0, 0.7, 0.5, 0.9], True, None),
+        (4, 7, 256, [0.6, 0.6, 0.0, 1.2], [0.6, 0.0, 0.0, 1.2], False, [1, 0, 1, 1]),
+        (3, 1, 512, [0.8, 0.0, 0.3], [0.8, 0.4, 0.3], True, None),
+        (2, 3, 320, [0.0, 0.0], [0.0, 0.0], False, [0, 1]),
+    ]
+    for ci, (B, K, V, tts, tqs, jit, hits_l) in enumerate(cfgs):
+        lp = (torch.randn(B, K + 1, V, generator=g) * 2).to(torch.bfloat16)
+        lq = (lp[:, :K].float() + 0.7 * torch.randn(B, K, V, generator=g)).to(torch.bfloat16)
+        spec = torch.randint(0, V, (B, K + 1), generator=g)
+        for b in range(B):
+            for j in range(K):
+                if tqs[b] > 0:
+                    spec[b, j + 1] = int(real_multinomial(torch.softmax(lq[b, j].float() / tqs[b], -1), 1, generator=g))
+                else:
+                    spec[b, j + 1] = int(lq[b, j].argmax())
+        uni = torch.rand(B, K, generator=g)
+        captured = []
+        torch.rand_like = lambda t, **kw: uni.to(t.dtype)
+        def fake_multinomial(p, n, **kw):
+            captured.append(p.clone())
+            return p.argmax(dim=-1, keepdim=True)
+        torch.multinomial = fake_multinomial
+        try:
+            hits = torch.tensor(hits_l) if hits_l is not None else None
+            suf, rec = vmod.verify(lp, lq, spec, torch.tensor(tts), torch.tensor(tqs), cache_hits=hits, jit_speculate=jit)
+        finally:
+            torch.rand_like, torch.multinomial = real_rand_like, real_multinomial
+        cases[f"c{ci}_lp"] = lp.view(torch.int16).numpy()
+        cases[f"c{ci}_lq"] = lq.view(torch.int16).numpy()
+        cases[f"c{ci}_spec"] = spec.numpy()
+        cases[f"c{ci}_uni"] = uni.numpy()
+        cases[f"c{ci}_tt"] = np.array(tts, dtype=np.float32)
+        cases[f"c{ci}_tq"] = np.array(tqs, dtype=np.float32)
+        cases[f"c{ci}_jit"] = np.array(int(jit))
+        if hits is not None:
+            cases[f"c{ci}_hits"] = hits.numpy().astype(np.int32)
+        cases[f"c{ci}_nacc"] = np.array([len(s) - 1 for s in suf], dtype=np.int32)
+        cases[f"c{ci}_rec_argmax"] = np.array(rec, dtype=np.int64)
+        cases[f"c{ci}_suffix_flat"] = np.array([t for s in suf for t in s], dtype=np.int64)
+    cases["n_cases"] = np.array(len(cfgs))
+    np.savez_compressed(OUT / "verify_mixed.npz", **cases)
+    print("verify_mixed ok")
+
+
 def gen_sampler(ssd):
     from ssd.layers.sampler import Sampler
 
@@ -404,8 +457,12 @@ def main():
         assert os.environ.get("TORCHDYNAMO_DISABLE") == "1"
         gen_layers(ssd, "eager")
         return
+    if tag == "mixed":  # incremental: only the per-row-temperature verify cases
+        gen_verify_mixed(ssd)
+        return
     gen_verify_t0(ssd)
     gen_verify_ratio(ssd)
+    gen_verify_mixed(ssd)
     gen_sampler(ssd)
     gen_layers(ssd, "compiled")
     gen_trace(ssd, "llama")

@@ -150,3 +150,24 @@ def test_baseline_config0_plumbing_1b_shapes_on_cpu():
         assert len(suf[0]) == K + 1  # identical draft: everything is accepted
         sd_tokens += suf[0]
     assert sd_tokens[:12] == ar_tokens[:12]
+
+
+def test_verify_mixed_rows_match_reference():
+    """Greedy and sampled rows in one batch, cache-hit gating, K = 1..7: accept counts, suffixes and the recovery rule
+    (mode of the distribution the reference hands to multinomial; greedy token on temp-0 rows) match the reference."""
+    z = load("verify_mixed.npz")
+    for c in range(int(z["n_cases"])):
+        lp, lq, spec = bf16(z[f"c{c}_lp"]), bf16(z[f"c{c}_lq"]), torch.from_numpy(z[f"c{c}_spec"])
+        tt, tq = torch.from_numpy(z[f"c{c}_tt"]), torch.from_numpy(z[f"c{c}_tq"])
+        jit = bool(int(z[f"c{c}_jit"]))
+        hits = torch.from_numpy(z[f"c{c}_hits"]) if f"c{c}_hits" in z else None
+        uni = torch.from_numpy(z[f"c{c}_uni"])
+        suf, rec, dbg = V.verify(lp, lq, spec, tt, tq, hits, jit, uni, return_debug=True)
+        assert [len(s) - 1 for s in suf] == z[f"c{c}_nacc"].tolist(), f"case {c}"
+        assert [t for s in suf for t in s] == z[f"c{c}_suffix_flat"].tolist(), f"case {c}"
+        for b in range(lp.shape[0]):
+            want = int(z[f"c{c}_rec_argmax"][b])
+            if float(tt[b]) > 0:
+                assert int(dbg["recovery_dists"][b].argmax()) == want, f"case {c} row {b}"
+            else:
+                assert rec[b] == want, f"case {c} row {b}"
