@@ -64,6 +64,21 @@ def is_stale() -> bool:
     return any(p.stat().st_mtime > t for p in sources() + headers())
 
 
+def build_trace_variant() -> Path:
+    """libssdk_trace.so: same sources with -DSSDK_TRACE_FINE (phase marks inside the kernels for tools/trace_step.py).
+    Loaded instead of libssdk.so when SSDK_LIB points at it; never used by the product path."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    inc, lib = _nccl_paths()
+    out = OUT_DIR / "libssdk_trace.so"
+    cmd = [nvcc, *NVCC_FLAGS, "-DSSDK_TRACE_FINE", *inc, "-o", str(out), *map(str, sources()), *lib, "-lcudart_static", "-ldl",
+           "-lrt", "-lpthread"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed for the trace variant")
+    return out
+
+
 def build(force: bool = False, verbose: bool = True) -> Path:
     if not force and not is_stale():
         return LIB
@@ -87,3 +102,5 @@ def build(force: bool = False, verbose: bool = True) -> Path:
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv)
     print(path)
+    if "--trace-variant" in sys.argv:
+        print(build_trace_variant())

@@ -22,7 +22,10 @@
 
 namespace ssdk {
 
-constexpr int kAttThreads = 128;
+// warps per CTA: 8 for the 32/64-row q tiles (four or two token slices per m-tile), 4 for single-m-tile decode.
+// One CTA per SM is resident, so the kernel is bound by the length of each warp's serial instruction chain (address
+// generation, softmax, epilogue merge) rather than by bandwidth: more warps = shorter chains.
+constexpr int attn_warps(int MT) { return MT == 1 ? 4 : 8; }
 constexpr int kAttChunk = 64;
 
 struct AttnParams {
@@ -35,6 +38,7 @@ struct AttnParams {
   float* part_o;                 // [B*Q*H, n_split, hd]
   float* part_lse;               // [B*Q*H, n_split]
   int B, Q, H, KV, block_size, max_blocks, n_split, TQ, n_qtiles;
+  int g_shift;                   // log2(H / KV) when the GQA ratio is a power of two, else -1
   float scale_log2;              // softmax scale * log2(e)
 };
 
@@ -71,9 +75,11 @@ SSDK_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 template <int HD, int MT>
-__global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
+__global__ void __launch_bounds__(attn_warps(MT) * 32) paged_attn_kernel(AttnParams p) {
+  constexpr int NW = attn_warps(MT);
+  constexpr int kAttThreads = NW * 32;
   constexpr int LDS = HD + 8;               // padded smem row (bf16 elements)
-  constexpr int TSL = 4 / MT;               // token slices per chunk
+  constexpr int TSL = NW / MT;              // token slices per chunk
   constexpr int TW = kAttChunk / TSL;       // tokens per warp per chunk (16 * MT)
   constexpr int NT = TW / 8;                // 8-token score tiles per warp
   constexpr int KS = HD / 16;               // k-steps over head_dim
@@ -176,12 +182,14 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
   if (ch_begin < ch_end) {
     load_chunk(ch_begin, 0);
     cp_async_commit();
+    if (threadIdx.x == 0) trace_fine(TRF_ATTN + 0);  // q + first chunk requested
     for (int ch = ch_begin; ch < ch_end; ++ch) {
       const int stage = (ch - ch_begin) & 1;
       if (ch + 1 < ch_end) load_chunk(ch + 1, stage ^ 1);
       cp_async_commit();
       cp_async_wait<1>();
       __syncthreads();
+      if (threadIdx.x == 0 && ch == ch_begin) trace_fine(TRF_ATTN + 1);  // first chunk landed
 
       const __nv_bfloat16* cK = sK + stage * kAttChunk * LDS;
       const __nv_bfloat16* cV = sV + stage * kAttChunk * LDS;
@@ -271,6 +279,7 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
   }
   cp_async_wait<0>();
   __syncthreads();
+  if (threadIdx.x == 0) trace_fine(TRF_ATTN + 2);  // chunk loop done
 
   // ---- finish row sums across the quad, merge token slices through smem ----
 #pragma unroll
@@ -278,22 +287,21 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
     lrow[h] += __shfl_xor_sync(0xffffffffu, lrow[h], 1);
     lrow[h] += __shfl_xor_sync(0xffffffffu, lrow[h], 2);
   }
-  constexpr int LDO = HD + 2;
-  float* sO = reinterpret_cast<float*>(att_smem);  // [4 warps][16 rows][LDO]: O | m | l   (fits: 4*16*130*4 = 33 KB)
+  // Row stride HD + 8 floats (= 8 banks mod 32): the 8-byte fragment stores of a half-warp (rows g = 0..3, column
+  // pairs t = 0..3) and the 16-byte row reads of the merge loop are both bank-conflict free.  With 8 warps the buffer
+  // is exactly as large as the K/V stages it reuses: 8 * 16 * (HD + 8) * 4 B.
+  constexpr int LDO = HD + 8;
+  float* sO = reinterpret_cast<float*>(att_smem);  // [NW warps][16 rows][LDO]: O | m | l
   {
     float* w = sO + warp * 16 * LDO;
 #pragma unroll
     for (int i = 0; i < ND; ++i) {
-      w[g * LDO + i * 8 + 2 * t] = o[i][0];
-      w[g * LDO + i * 8 + 2 * t + 1] = o[i][1];
-      w[(g + 8) * LDO + i * 8 + 2 * t] = o[i][2];
-      w[(g + 8) * LDO + i * 8 + 2 * t + 1] = o[i][3];
+      *reinterpret_cast<float2*>(w + g * LDO + i * 8 + 2 * t) = make_float2(o[i][0], o[i][1]);
+      *reinterpret_cast<float2*>(w + (g + 8) * LDO + i * 8 + 2 * t) = make_float2(o[i][2], o[i][3]);
     }
     if (t == 0) {
-      w[g * LDO + HD] = mrow[0];
-      w[g * LDO + HD + 1] = lrow[0];
-      w[(g + 8) * LDO + HD] = mrow[1];
-      w[(g + 8) * LDO + HD + 1] = lrow[1];
+      *reinterpret_cast<float2*>(w + g * LDO + HD) = make_float2(mrow[0], lrow[0]);
+      *reinterpret_cast<float2*>(w + (g + 8) * LDO + HD) = make_float2(mrow[1], lrow[1]);
     }
   }
   __syncthreads();
@@ -310,13 +318,16 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
 #pragma unroll
       for (int sl = 0; sl < TSL; ++sl) {
         const float* w = sO + ((sl * MT + mt) * 16 + rr) * LDO;
-        const float wgt = exp2f(w[HD] - mmax);
-        acc.x += w[d] * wgt; acc.y += w[d + 1] * wgt; acc.z += w[d + 2] * wgt; acc.w += w[d + 3] * wgt;
-        l += w[HD + 1] * wgt;
+        const float2 ml = *reinterpret_cast<const float2*>(w + HD);
+        const float4 v = *reinterpret_cast<const float4*>(w + d);
+        const float wgt = exp2f(ml.x - mmax);
+        acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+        l += ml.y * wgt;
       }
     }
-    const int row_q = b * p.Q + qt * p.TQ + r / G;
-    const int head = kvh * G + r % G;
+    const int rt = (p.g_shift >= 0) ? (r >> p.g_shift) : r / G;  // token inside the tile; r - rt * G = head of the group
+    const int row_q = b * p.Q + qt * p.TQ + rt;
+    const int head = kvh * G + (r - rt * G);
     const float inv = (l > 0.f) ? 1.f / l : 0.f;
     acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
     if (p.n_split == 1) {
@@ -329,6 +340,7 @@ __global__ void __launch_bounds__(kAttThreads) paged_attn_kernel(AttnParams p) {
       if (d == 0) p.part_lse[pr] = (l > 0.f) ? mmax + log2f(l) : -INFINITY;
     }
   }
+  if (threadIdx.x == 0) trace_fine(TRF_ATTN + 3);  // partials / output stored
 }
 
 // merge split-KV partials: out = sum_s 2^(lse_s - max) o_s / sum_s 2^(lse_s - max).
@@ -366,6 +378,7 @@ __global__ void attn_combine_kernel(AttnParams p, int hd) {
     v[u] = (mine && u < n_active) ? __ldcg(reinterpret_cast<const float4*>(p.part_o + (row * p.n_split + u) * hd) + d4)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
+  if (threadIdx.x == 0) trace_fine(TRF_COMB + 0);  // weights ready, first batch requested
   if (!mine) return;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s0 = 0; s0 < n_active; s0 += 8) {
@@ -384,6 +397,7 @@ __global__ void attn_combine_kernel(AttnParams p, int hd) {
   __nv_bfloat16* dst = p.out + row * hd + d4 * 4;
   *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(acc.x, acc.y);
   *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(acc.z, acc.w);
+  if (threadIdx.x == 0) trace_fine(TRF_COMB + 1);
 }
 
 }  // namespace ssdk

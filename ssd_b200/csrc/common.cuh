@@ -243,8 +243,10 @@ SSDK_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_d
 // the real, PDL-overlapped, per-kernel increments of the critical path inside a graph replay —
 // something ncu's serialised replay cannot show.  Enabled with ssdk_debug_trace().
 // ----------------------------------------------------------------------------------
-__device__ unsigned long long* g_trace_buf = nullptr;  // [cap][2] = (id, time ns)
-__device__ unsigned g_trace_cap = 0;
+// The switch lives in constant memory: when tracing is off a kernel pays one uniform constant load, not a dependent
+// global load on its first warp.
+__constant__ unsigned long long* g_trace_buf = nullptr;  // [cap][2] = (id, time ns)
+__constant__ unsigned g_trace_cap = 0;
 __device__ unsigned g_trace_n = 0;
 enum { TR_PREP = 1, TR_NORM, TR_GEMM, TR_ROPE, TR_ATTN, TR_SAMPLE, TR_VERIFY, TR_MISC };
 SSDK_DEVINL void trace_mark(int id) {
@@ -257,6 +259,16 @@ SSDK_DEVINL void trace_mark(int id) {
     g_trace_buf[2 * slot] = (unsigned long long)id;
     g_trace_buf[2 * slot + 1] = t;
   }
+}
+// Phase marks inside a kernel (ids >= 16, tools/trace_step.py prints the mean gaps between them).  Each mark costs the
+// marking thread an atomic round trip (~0.6 us), so they are compiled in only with -DSSDK_TRACE_FINE.
+enum { TRF_ATTN = 16, TRF_NORM = 24, TRF_ROPE = 32, TRF_COMB = 40, TRF_GEMM = 48 };
+SSDK_DEVINL void trace_fine(int id) {
+#ifdef SSDK_TRACE_FINE
+  trace_mark(id);
+#else
+  (void)id;
+#endif
 }
 
 SSDK_DEVINL bool elect_one() {

@@ -34,7 +34,9 @@ SSDK_DEVINL float gemm_out_at(const GemmOut& g, int m, int n) {
   }
   return bf16_round(acc);
 }
-// 8 consecutive columns starting at n (n % 8 == 0)
+// 8 consecutive columns starting at n (n % 8 == 0).  NB = slabs requested per batch: 8 keeps 16 float4 loads
+// (64 registers) in flight; callers that hold more live state per thread use 4.
+template <int NB = 8>
 SSDK_DEVINL void gemm_out_at8(const GemmOut& g, int m, int n, float* f) {
   if (g.S == 0) {
     uint4 v = *reinterpret_cast<const uint4*>(g.dense + (size_t)m * g.N + n);
@@ -45,10 +47,10 @@ SSDK_DEVINL void gemm_out_at8(const GemmOut& g, int m, int n, float* f) {
   for (int i = 0; i < 8; ++i) f[i] = 0.f;
   const float* base = g.partial + (size_t)m * g.N + n;
   const size_t stride = (size_t)g.M * g.N;
-  for (int s0 = 0; s0 < g.S; s0 += 8) {
-    float4 a[8], b[8];
+  for (int s0 = 0; s0 < g.S; s0 += NB) {
+    float4 a[NB], b[NB];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < NB; ++u) {
       if (s0 + u < g.S) {
         const float4* p = reinterpret_cast<const float4*>(base + (size_t)(s0 + u) * stride);
         a[u] = __ldcg(p);
@@ -59,7 +61,7 @@ SSDK_DEVINL void gemm_out_at8(const GemmOut& g, int m, int n, float* f) {
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < NB; ++u) {
       f[0] += a[u].x; f[1] += a[u].y; f[2] += a[u].z; f[3] += a[u].w;
       f[4] += b[u].x; f[5] += b[u].y; f[6] += b[u].z; f[7] += b[u].w;
     }
@@ -81,19 +83,19 @@ SSDK_DEVINL void gemm_out_at2x2(const GemmOut& g, int m, int a, int b, float* fa
   const size_t stride = (size_t)g.M * g.N;
   for (int s0 = 0; s0 < g.S; s0 += 8) {
     float2 va[8], vb[8];
+    // unconditional loads from a clamped slab index (straight-line code: all 16 requests are in flight together), the
+    // out-of-range copies are dropped by the selects below
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      if (s0 + u < g.S) {
-        va[u] = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(s0 + u) * stride + a));
-        vb[u] = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(s0 + u) * stride + b));
-      } else {
-        va[u] = make_float2(0.f, 0.f);
-        vb[u] = va[u];
-      }
+      const float* row = base + (size_t)min(s0 + u, g.S - 1) * stride;
+      va[u] = __ldcg(reinterpret_cast<const float2*>(row + a));
+      vb[u] = __ldcg(reinterpret_cast<const float2*>(row + b));
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      fa[0] += va[u].x; fa[1] += va[u].y; fb[0] += vb[u].x; fb[1] += vb[u].y;
+      const bool in = s0 + u < g.S;
+      fa[0] += in ? va[u].x : 0.f; fa[1] += in ? va[u].y : 0.f;
+      fb[0] += in ? vb[u].x : 0.f; fb[1] += in ? vb[u].y : 0.f;
     }
   }
   fa[0] = bf16_round(fa[0]); fa[1] = bf16_round(fa[1]); fb[0] = bf16_round(fb[0]); fb[1] = bf16_round(fb[1]);
@@ -168,11 +170,80 @@ struct NormParams {
   int d;
 };
 
-// blockDim.x = d/16..d/8 (<= 512): every thread owns at most TWO 8-element slices that stay in registers between the passes,
-// and all of its loads (weights, residual, GEMM partials / all-reduce words) are in flight together — the kernel costs
-// ~2 L2 round trips + one block reduction.  Rows wider than 8192 fall back to a shared-memory staged loop.
+// One 8-element slice of the row: x = (all-reduced | embedded | GEMM) input + residual; writes the new residual.
+template <int NB>
+SSDK_DEVINL void norm_slice(const NormParams& p, int m, int i, const uint8_t* symm_slots, unsigned symm_e,
+                            const __nv_bfloat16* erow, bool zero_row, float* x) {
+  const int d = p.d;
+  uint4 res = make_uint4(0, 0, 0, 0);
+  if (p.residual_in) res = *reinterpret_cast<const uint4*>(p.residual_in + (size_t)m * d + i);
+  if (symm_slots) {
+    // sum the ranks' bf16 contributions in rank order (identical on every rank), fp32 accumulate, one bf16 rounding.
+    // 8 elements = 4 words {2 x bf16, flag} = two 16-byte loads per rank; all ranks' loads are issued before any flag is
+    // looked at, and the pass is repeated until all four flags of every rank show this epoch.
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    const size_t word0 = ((size_t)m * d + i) / 2;
+    uint4 lo[kSymmMaxRanks], hi[kSymmMaxRanks];
+    const long long t0 = clock64();
+    bool ready = false;
+    while (!ready) {
+#pragma unroll
+      for (int r = 0; r < kSymmMaxRanks; ++r) {
+        if (r < p.symm.n_ranks) {
+          const uint4* src = reinterpret_cast<const uint4*>(symm_slots + (size_t)r * p.symm.slot_bytes) + word0 / 2;
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo[r].x), "=r"(lo[r].y), "=r"(lo[r].z), "=r"(lo[r].w) : "l"(src));
+          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi[r].x), "=r"(hi[r].y), "=r"(hi[r].z), "=r"(hi[r].w) : "l"(src + 1));
+        }
+      }
+      ready = true;
+#pragma unroll
+      for (int r = 0; r < kSymmMaxRanks; ++r)
+        if (r < p.symm.n_ranks)
+          ready = ready && lo[r].y == symm_e && lo[r].w == symm_e && hi[r].y == symm_e && hi[r].w == symm_e;
+      if (!ready && clock64() - t0 > 8000000000LL) __trap();
+    }
+#pragma unroll
+    for (int r = 0; r < kSymmMaxRanks; ++r) {
+      if (r < p.symm.n_ranks) {
+        const uint32_t w4[4] = {lo[r].x, lo[r].z, hi[r].x, hi[r].z};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
+          x[2 * q] += c.x;
+          x[2 * q + 1] += c.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = bf16_round(x[j]);
+  } else if (p.ids) {
+    if (zero_row) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    } else {
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + i), x);
+    }
+  } else {
+    gemm_out_at8<NB>(p.x, m, i, x);
+  }
+  if (p.residual_in) {
+    float r[8];
+    unpack_bf16x8(res, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += r[j];
+  }
+  if (p.residual_out) *reinterpret_cast<uint4*>(p.residual_out + (size_t)m * d + i) = pack_bf16x8(x);
+}
+
+// SLICES = 1 / 2: the row is register-resident, d <= SLICES * 8 * blockDim.x; every thread issues all the loads of a slice
+// (weights, residual, <= 8 / 4 split-K slabs or all ranks' all-reduce words) before it uses any of them, so a slice costs
+// one L2 round trip; the kernel is ~SLICES round trips + one block reduction.  SLICES = 0: any d, row staged in shared
+// memory.  (With a single instantiation ptxas ran out of its 128 registers at 512 threads and serialised the slab loads:
+// one round trip per slab, 3-4 us per call.)
+template <int SLICES>
 __global__ void __launch_bounds__(512) add_rmsnorm_kernel(NormParams p) {
-  extern __shared__ float rbuf[];  // d floats (only used when d > 8 * blockDim.x)
+  extern __shared__ float rbuf[];  // d floats (SLICES == 0 only)
   __shared__ float red[32];
   pdl_launch_dependents();
   // All-reduce consumers after a row-parallel GEMM are pure dataflow: every input word (including THIS rank's own
@@ -199,97 +270,54 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(NormParams p) {
     else erow = p.embed + (size_t)id * d;
   }
   float ss = 0.f;
-  const bool single = (int)blockDim.x * 16 >= d;  // <= 2 slices per thread: keep them in registers
-  float xreg[2][8], wreg[2][8];
-  if (single && p.y) {
+  if constexpr (SLICES > 0) {
+    constexpr int NB = (SLICES == 1) ? 8 : 4;
+    float xreg[SLICES][8];
+    uint4 wpk[SLICES];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < SLICES; ++c) {
       const int i = (c * blockDim.x + threadIdx.x) * 8;
-      if (i < d) unpack_bf16x8(*reinterpret_cast<const uint4*>(p.w + i), wreg[c]);
+      if (i < d && p.y) wpk[c] = *reinterpret_cast<const uint4*>(p.w + i);
     }
-  }
-  int chunk = 0;
-  for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8, ++chunk) {
-    float x[8];
-    if (symm_slots) {
-      // sum the ranks' bf16 contributions in rank order (identical on every rank), fp32 accumulate, one bf16 rounding.
-      // 8 elements = 4 words {2 x bf16, flag} = two 16-byte loads per rank; spin until all four flags show this epoch.
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = 0.f;
-      const size_t word0 = ((size_t)m * d + i) / 2;
-      uint4 lo[kSymmMaxRanks], hi[kSymmMaxRanks];
-      const long long t0 = clock64();
-      bool ready = false;
-      while (!ready) {
-        ready = true;
+    for (int c = 0; c < SLICES; ++c) {
+      const int i = (c * blockDim.x + threadIdx.x) * 8;
+      if (i < d) {
+        norm_slice<NB>(p, m, i, symm_slots, symm_e, erow, zero_row, xreg[c]);
 #pragma unroll
-        for (int r = 0; r < kSymmMaxRanks; ++r) {
-          if (r < p.symm.n_ranks) {
-            const uint4* src = reinterpret_cast<const uint4*>(symm_slots + (size_t)r * p.symm.slot_bytes) + word0 / 2;
-            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo[r].x), "=r"(lo[r].y), "=r"(lo[r].z), "=r"(lo[r].w) : "l"(src));
-            asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi[r].x), "=r"(hi[r].y), "=r"(hi[r].z), "=r"(hi[r].w) : "l"(src + 1));
-            ready = ready && lo[r].y == symm_e && lo[r].w == symm_e && hi[r].y == symm_e && hi[r].w == symm_e;
-          }
-        }
-        if (!ready && clock64() - t0 > 8000000000LL) __trap();
+        for (int j = 0; j < 8; ++j) ss += xreg[c][j] * xreg[c][j];
       }
-#pragma unroll
-      for (int r = 0; r < kSymmMaxRanks; ++r) {
-        if (r < p.symm.n_ranks) {
-          const uint32_t w4[4] = {lo[r].x, lo[r].z, hi[r].x, hi[r].z};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
-            x[2 * q] += c.x;
-            x[2 * q + 1] += c.y;
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = bf16_round(x[j]);
-    } else if (p.ids) {
-      if (zero_row) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = 0.f;
-      } else {
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + i), x);
-      }
-    } else {
-      gemm_out_at8(p.x, m, i, x);
     }
-    if (p.residual_in) {
-      float r[8];
-      unpack_bf16x8(*reinterpret_cast<const uint4*>(p.residual_in + (size_t)m * d + i), r);
+    if (threadIdx.x == 0) trace_fine(TRF_NORM + 0);  // inputs arrived (thread 0's slices)
+    ss = block_sum(ss, red);
+    if (threadIdx.x == 0) trace_fine(TRF_NORM + 1);  // row statistic reduced
+    const float rstd = rsqrtf(ss / (float)d + p.eps);
+    if (p.y) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] += r[j];
-    }
-    if (p.residual_out) *reinterpret_cast<uint4*>(p.residual_out + (size_t)m * d + i) = pack_bf16x8(x);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (single) {
-        if (chunk == 0) xreg[0][j] = x[j];
-        else xreg[1][j] = x[j];
-      } else {
-        rbuf[i + j] = x[j];
-      }
-      ss += x[j] * x[j];
-    }
-  }
-  ss = block_sum(ss, red);
-  const float rstd = rsqrtf(ss / (float)d + p.eps);
-  if (p.y) {
-    if (single) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < SLICES; ++c) {
         const int i = (c * blockDim.x + threadIdx.x) * 8;
         if (i < d) {
-          float o[8];
+          float w[8], o[8];
+          unpack_bf16x8(wpk[c], w);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = xreg[c][j] * rstd * wreg[c][j];
+          for (int j = 0; j < 8; ++j) o[j] = xreg[c][j] * rstd * w[j];
           *reinterpret_cast<uint4*>(p.y + (size_t)m * d + i) = pack_bf16x8(o);
         }
       }
-    } else {
+    }
+  } else {
+    for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
+      float x[8];
+      norm_slice<4>(p, m, i, symm_slots, symm_e, erow, zero_row, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        rbuf[i + j] = x[j];
+        ss += x[j] * x[j];
+      }
+    }
+    ss = block_sum(ss, red);
+    const float rstd = rsqrtf(ss / (float)d + p.eps);
+    if (p.y) {
       for (int i = threadIdx.x * 8; i < d; i += blockDim.x * 8) {
         float w[8], o[8];
         unpack_bf16x8(*reinterpret_cast<const uint4*>(p.w + i), w);
@@ -299,6 +327,7 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(NormParams p) {
       }
     }
   }
+  if (threadIdx.x == 0) trace_fine(TRF_NORM + 2);
 }
 
 // ----------------------------------------------------------------------------------
@@ -378,65 +407,84 @@ struct RopeParams {
   int heads, kv_heads, head_dim;
 };
 
+// HD is a template parameter so that the per-lane element pairs are static registers (a run-time head_dim turned the
+// x1/x2 arrays into local memory and made ptxas recycle the load registers, i.e. one L2 round trip per split-K slab).
+template <int HD>
 __global__ void __launch_bounds__(128) rope_store_kernel(RopeParams p) {
+  constexpr int HALF = HD / 2;
+  constexpr int NP = (HALF + 63) / 64;  // (i, i+1) / (i + HALF, i + HALF + 1) pairs per lane, i = 2 * lane + 64 * t
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(TR_ROPE);
   const int m = blockIdx.x;
   const int head = blockIdx.y * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const int H = p.heads, KV = p.kv_heads, hd = p.head_dim, half = hd >> 1;
+  const int H = p.heads, KV = p.kv_heads;
   if (head >= H + 2 * KV) return;
   const int kind = head < H ? 0 : (head < H + KV ? 1 : 2);  // q, k, v
-  const int col0 = head * hd;
+  const int col0 = head * HD;
+  // the slot, the position and the projection values are requested together; nothing below waits for one of them
+  // before the others are in flight
   const int slot = p.slot_mapping[m];
+  const long long pos = p.positions[m];
 
+  float x1[NP][2], x2[NP][2];
+  float ss = 0.f;
+#pragma unroll
+  for (int t = 0; t < NP; ++t) {
+    const int i = 2 * lane + 64 * t;
+    if (i < HALF) {
+      gemm_out_at2x2(p.qkv, m, col0 + i, col0 + HALF + i, x1[t], x2[t]);
+      ss += x1[t][0] * x1[t][0] + x1[t][1] * x1[t][1] + x2[t][0] * x2[t][0] + x2[t][1] * x2[t][1];
+    } else {
+      x1[t][0] = x1[t][1] = x2[t][0] = x2[t][1] = 0.f;
+    }
+  }
+  if (kind != 0 && slot < 0) return;
   if (kind == 2) {
-    if (slot < 0) return;
-    __nv_bfloat16* dst = p.v_cache + ((size_t)slot * KV + (head - H - KV)) * hd;
-    for (int i = 2 * lane; i < half; i += 64) {  // same (i, i + half) split as q/k: all loads of a lane in flight
-      float a[2], b[2];
-      gemm_out_at2x2(p.qkv, m, col0 + i, col0 + half + i, a, b);
-      *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(a[0], a[1]);
-      *reinterpret_cast<__nv_bfloat162*>(dst + half + i) = __floats2bfloat162_rn(b[0], b[1]);
+    __nv_bfloat16* dst = p.v_cache + ((size_t)slot * KV + (head - H - KV)) * HD;
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+      const int i = 2 * lane + 64 * t;
+      if (i < HALF) {
+        *reinterpret_cast<__nv_bfloat162*>(dst + i) = __floats2bfloat162_rn(x1[t][0], x1[t][1]);
+        *reinterpret_cast<__nv_bfloat162*>(dst + HALF + i) = __floats2bfloat162_rn(x2[t][0], x2[t][1]);
+      }
     }
     return;
   }
-  if (kind == 1 && slot < 0) return;
-
-  // each lane owns the element pairs (i, i+1) and (i + half, i + half + 1), i = 2*lane (+64 for hd = 256)
-  float x1[2][2], x2[2][2];
-  float ss = 0.f;
-  int np = 0;
-  for (int i = 2 * lane; i < half; i += 64, ++np) {
-    gemm_out_at2x2(p.qkv, m, col0 + i, col0 + half + i, x1[np], x2[np]);
-    ss += x1[np][0] * x1[np][0] + x1[np][1] * x1[np][1] + x2[np][0] * x2[np][0] + x2[np][1] * x2[np][1];
-  }
+  if (threadIdx.x == 0) trace_fine(TRF_ROPE + 0);  // projection row reduced from the partials
   const __nv_bfloat16* nw = (kind == 0) ? p.q_norm_w : p.k_norm_w;
   if (nw) {
     ss = warp_sum(ss);
-    const float rstd = rsqrtf(ss / (float)hd + p.norm_eps);
-    int t = 0;
-    for (int i = 2 * lane; i < half; i += 64, ++t) {
+    const float rstd = rsqrtf(ss / (float)HD + p.norm_eps);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        x1[t][e] = bf16_round(x1[t][e] * rstd * bf2f(nw[i + e]));
-        x2[t][e] = bf16_round(x2[t][e] * rstd * bf2f(nw[half + i + e]));
+    for (int t = 0; t < NP; ++t) {
+      const int i = 2 * lane + 64 * t;
+      if (i < HALF) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          x1[t][e] = bf16_round(x1[t][e] * rstd * bf2f(nw[i + e]));
+          x2[t][e] = bf16_round(x2[t][e] * rstd * bf2f(nw[HALF + i + e]));
+        }
       }
     }
   }
-  const long long pos = p.positions[m];
-  const float* cs = p.rope_table + (size_t)pos * hd;
-  __nv_bfloat16* dst = (kind == 0) ? p.q_out + (size_t)m * H * hd + (size_t)head * hd
-                                   : p.k_cache + ((size_t)slot * KV + (head - H)) * hd;
-  int t = 0;
-  for (int i = 2 * lane; i < half; i += 64, ++t) {
-    const float2 c = *reinterpret_cast<const float2*>(cs + i), sn = *reinterpret_cast<const float2*>(cs + half + i);
-    *reinterpret_cast<__nv_bfloat162*>(dst + i) =
-        __floats2bfloat162_rn(x1[t][0] * c.x - x2[t][0] * sn.x, x1[t][1] * c.y - x2[t][1] * sn.y);
-    *reinterpret_cast<__nv_bfloat162*>(dst + half + i) =
-        __floats2bfloat162_rn(x2[t][0] * c.x + x1[t][0] * sn.x, x2[t][1] * c.y + x1[t][1] * sn.y);
+  const float* cs = p.rope_table + (size_t)pos * HD;
+  __nv_bfloat16* dst = (kind == 0) ? p.q_out + (size_t)m * H * HD + (size_t)head * HD
+                                   : p.k_cache + ((size_t)slot * KV + (head - H)) * HD;
+#pragma unroll
+  for (int t = 0; t < NP; ++t) {
+    const int i = 2 * lane + 64 * t;
+    if (i < HALF) {
+      const float2 c = *reinterpret_cast<const float2*>(cs + i), sn = *reinterpret_cast<const float2*>(cs + HALF + i);
+      *reinterpret_cast<__nv_bfloat162*>(dst + i) =
+          __floats2bfloat162_rn(x1[t][0] * c.x - x2[t][0] * sn.x, x1[t][1] * c.y - x2[t][1] * sn.y);
+      *reinterpret_cast<__nv_bfloat162*>(dst + HALF + i) =
+          __floats2bfloat162_rn(x2[t][0] * c.x + x1[t][0] * sn.x, x2[t][1] * c.y + x1[t][1] * sn.y);
+    }
   }
+  if (threadIdx.x == 0) trace_fine(TRF_ROPE + 1);
 }
 
 // ----------------------------------------------------------------------------------

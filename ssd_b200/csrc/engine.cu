@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -130,7 +131,22 @@ static int num_sms() {
 }
 // add_rmsnorm_kernel geometry: <= 2 register-resident 8-element slices per thread (512 threads), smem staging beyond
 static int norm_threads(int d) { return std::max(32, std::min(512, ((d / 8 + 31) / 32) * 32)); }
-static size_t norm_smem(int d) { return d > 8192 ? (size_t)d * 4 : 0; }
+static int launch_norm(Launcher& L, int M, int d, const NormParams& np) {
+  const int threads = norm_threads(d);
+  const int slices = (d + 8 * threads - 1) / (8 * threads);
+  if (slices == 1) return L.go(add_rmsnorm_kernel<1>, dim3(M), dim3(threads), 0, np);
+  if (slices == 2) return L.go(add_rmsnorm_kernel<2>, dim3(M), dim3(threads), 0, np);
+  return L.go(add_rmsnorm_kernel<0>, dim3(M), dim3(threads), (size_t)d * 4, np);
+}
+static int launch_rope(Launcher& L, int M, const RopeParams& rp) {
+  const dim3 grid(M, (rp.heads + 2 * rp.kv_heads + 3) / 4), block(128);
+  switch (rp.head_dim) {
+    case 64: return L.go(rope_store_kernel<64>, grid, block, 0, rp);
+    case 128: return L.go(rope_store_kernel<128>, grid, block, 0, rp);
+    case 256: return L.go(rope_store_kernel<256>, grid, block, 0, rp);
+    default: return fail("unsupported head_dim %d for RoPE (64, 128 and 256 are built)", rp.head_dim);
+  }
+}
 static int umma_n_for(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : 64); }
 
 static int auto_splits(int tiles, int num_kb) {
@@ -394,7 +410,9 @@ struct Fwd {
 static int attn_plan(const Model& m, int B, int Q, int* TQ, int* MT, int* nqt, int* nsplit, int max_ctx) {
   const int G = m.H / m.KV;
   if (G < 1 || G > 16 || (m.H % m.KV) != 0) return fail("unsupported GQA ratio %d", G);
-  int tq = std::min(Q, std::max(1, 64 / G));
+  // q tile of <= 32 rows (two 16-row MMA tiles, 8 warps = 4 token slices each): measured 7.3 us per 70B verify layer
+  // against 8.1 us with one 56-row tile and 9.5 us with 16-row tiles (profiles/r01_small_kernels.md)
+  int tq = std::min(Q, std::max(1, 32 / G));
   int R = G * tq;
   int mt = (R + 15) / 16;
   if (mt == 3) mt = 4;
@@ -418,7 +436,7 @@ static int launch_attn_inst(Launcher& L, const AttnParams& p, dim3 grid) {
     CK(cudaFuncSetAttribute(paged_attn_kernel<HD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  return L.go(paged_attn_kernel<HD, MT>, grid, dim3(kAttThreads), smem, p);
+  return L.go(paged_attn_kernel<HD, MT>, grid, dim3(attn_warps(MT) * 32), smem, p);
 }
 static int launch_attn(Launcher& L, const AttnParams& p, int hd, int MT, dim3 grid) {
   if (hd == 128 && MT == 1) return launch_attn_inst<128, 1>(L, p, grid);
@@ -441,6 +459,9 @@ static int enqueue_attention(Launcher& L, const bf16* q, const bf16* kc, const b
   (void)counters;
   a.B = B; a.Q = Q; a.H = H; a.KV = KV; a.block_size = block_size; a.max_blocks = max_blocks;
   a.n_split = nsplit; a.TQ = TQ; a.n_qtiles = nqt;
+  a.g_shift = -1;
+  for (int sft = 0; sft < 5; ++sft)
+    if ((H / KV) == (1 << sft)) a.g_shift = sft;
   a.scale_log2 = scale * 1.4426950408889634f;
   CKI(launch_attn(L, a, hd, MT, dim3(KV, nsplit, B * nqt)));
   if (nsplit > 1) CKI(L.go(attn_combine_kernel, dim3(B * Q * H), dim3(32), 0, a, hd));
@@ -577,7 +598,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
           np.symm = symm_in(e, ar_idx++);
         } else {
           ep.eps = m.cfg.rms_eps; ep.d = m.d; ep.residual_out = w.dense_tmp;  // y = null: gather only
-          CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), ep));
+          CKI(launch_norm(L, M, m.d, ep));
           CKN(ncclAllReduce(w.dense_tmp, w.dense_tmp, (size_t)M * m.d, ncclBfloat16, ncclSum, e->comm, L.st));
           L.barrier_op();
           np.x.dense = w.dense_tmp; np.x.S = 0; np.x.M = M; np.x.N = m.d;
@@ -588,7 +609,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
       if (prev_symm) np.symm = symm_in(e, prev_idx, true);
       np.residual_in = w.residual;
     }
-    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), np));
+    CKI(launch_norm(L, M, m.d, np));
 
     // ---- QKV projection -> RoPE (+qk norm) -> KV store ----
     int S = 1;
@@ -603,7 +624,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     rp.k_cache = m.k_cache + (size_t)l * cache_layer_stride;
     rp.v_cache = m.v_cache + (size_t)l * cache_layer_stride;
     rp.heads = m.H; rp.kv_heads = m.KV; rp.head_dim = m.hd;
-    CKI(L.go(rope_store_kernel, dim3(M, (m.H + 2 * m.KV + 3) / 4), dim3(128), 0, rp));
+    CKI(launch_rope(L, M, rp));
 
     // ---- attention over the paged cache ----
     CKI(enqueue_attention(L, w.q, rp.k_cache, rp.v_cache, f.block_tables, w.context_lens, w.attn_out, w.att_o,
@@ -631,7 +652,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     pn.x = oproj; pn.residual_in = w.residual; pn.w = lw.post_norm; pn.eps = m.cfg.rms_eps;
     if (oproj_symm) pn.symm = symm_in(e, oproj_idx, true);
     pn.y = w.hidden; pn.residual_out = w.residual; pn.d = m.d;
-    CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), pn));
+    CKI(launch_norm(L, M, m.d, pn));
 
     // ---- MLP: gate|up with fused SiLU*mul when the tile count fills the machine ----
     const int silu_tiles = (m.ffn + 63) / 64;
@@ -661,7 +682,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
   fn.x = prev; fn.residual_in = w.residual; fn.w = m.final_norm; fn.eps = m.cfg.rms_eps; fn.y = w.hidden;
   if (prev_symm) fn.symm = symm_in(e, prev_idx, true);
   fn.residual_out = nullptr; fn.d = m.d;
-  CKI(L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(m.d)), norm_smem(m.d), fn));
+  CKI(launch_norm(L, M, m.d, fn));
 
   // ---- lm_head ----
   if (f.logits_mode != 0) {
@@ -868,7 +889,7 @@ static int init_kernel_attrs() {
   CK(cudaFuncSetAttribute(paged_attn_kernel<HD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * kAttChunk * (HD + 8) * 2));
   SSDK_ATTR_A(128, 1) SSDK_ATTR_A(128, 2) SSDK_ATTR_A(128, 4) SSDK_ATTR_A(64, 1) SSDK_ATTR_A(64, 2) SSDK_ATTR_A(64, 4)
 #undef SSDK_ATTR_A
-  CK(cudaFuncSetAttribute(add_rmsnorm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaFuncSetAttribute(add_rmsnorm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   return 0;
 }
 
@@ -1291,7 +1312,7 @@ int ssdk_rmsnorm(const void* x, const void* residual_in, const void* w, float ep
   np.x.dense = (const bf16*)x; np.x.S = 0; np.x.M = M; np.x.N = d;
   np.residual_in = (const bf16*)residual_in; np.w = (const bf16*)w; np.eps = eps;
   np.y = (bf16*)y; np.residual_out = (bf16*)residual_out; np.d = d;
-  return L.go(add_rmsnorm_kernel, dim3(M), dim3(norm_threads(d)), norm_smem(d), np);
+  return launch_norm(L, M, d, np);
 }
 
 int ssdk_rope_store_kv(const void* qkv, const int64_t* positions, const int32_t* slot_mapping, const float* rope_table,
@@ -1307,7 +1328,7 @@ int ssdk_rope_store_kv(const void* qkv, const int64_t* positions, const int32_t*
   rp.q_norm_w = (const bf16*)q_norm_w; rp.k_norm_w = (const bf16*)k_norm_w; rp.norm_eps = norm_eps;
   rp.q_out = (bf16*)q_out; rp.k_cache = (bf16*)k_cache; rp.v_cache = (bf16*)v_cache;
   rp.heads = heads; rp.kv_heads = kv_heads; rp.head_dim = head_dim;
-  return L.go(rope_store_kernel, dim3(M, (heads + 2 * kv_heads + 3) / 4), dim3(128), 0, rp);
+  return launch_rope(L, M, rp);
 }
 
 int ssdk_silu_mul(const void* gate_up, void* out, int M, int ffn, void* stream) {

@@ -160,6 +160,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     const int row = q * 32 + lane;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) trace_fine(TRF_GEMM + 0);  // CTA 0's accumulator complete
     uint32_t r[UMMA_N];
 #pragma unroll
     for (int c = 0; c < UMMA_N / 16; ++c) tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(q * 32) << 16) + c * 16, r + c * 16);
@@ -207,6 +208,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 64) trace_fine(TRF_GEMM + 1);  // CTA 0's epilogue stored
   if (warp == 1) tmem_dealloc(tmem_d, Cfg::kTmemCols);
 }
 

@@ -107,7 +107,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                 raise RuntimeError(f"libssdk.so is missing and could not be built: {exc}") from exc
     if not _LIB_PATH.exists():
         raise RuntimeError(f"{_LIB_PATH} not found — run `python -m ssd_b200.build`; there is no CPU fallback")
-    lib = C.CDLL(str(_LIB_PATH), mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
+    path = os.environ.get("SSDK_LIB") or str(_LIB_PATH)  # SSDK_LIB: an alternative build of the same library (trace variant)
+    lib = C.CDLL(path, mode=os.RTLD_GLOBAL if hasattr(os, "RTLD_GLOBAL") else C.DEFAULT_MODE)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res

@@ -17,10 +17,11 @@ world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get(
 torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-workload = sys.argv[1] if len(sys.argv) > 1 else "8b"
+workload = sys.argv[1] if len(sys.argv) > 1 else "8b"   # "70b:8" = 70B dimensions with 8 layers (quick to set up)
+workload, _, nl = workload.partition(":")
 shapes = {"8b": ("llama-3.1-8b", "llama-3.2-1b"), "70b": ("llama-3.1-70b", "llama-3.2-1b")}[workload]
 root = tempfile.mkdtemp()
-llm = LLM(synth.make_model_dir(root, shapes[0], "target"), speculate=True, draft=synth.make_model_dir(root, shapes[1], "draft"),
+llm = LLM(synth.make_model_dir(root, shapes[0], "target", layers=int(nl) if nl else None), speculate=True, draft=synth.make_model_dir(root, shapes[1], "draft"),
           speculate_k=6, num_gpus=world, max_num_seqs=1, max_model_len=4096, jit_speculate=True, use_pdl=("--no-pdl" not in sys.argv))
 r = llm.runner
 random.seed(0)
@@ -32,7 +33,7 @@ r.stage([len(prompt)], [rec], [bt], [bt], [0.0], [0.0])
 for _ in range(3):
     r.step_resident(1)
 torch.cuda.synchronize()
-cap = 4096
+cap = 32768
 buf = torch.zeros(cap, 2, dtype=torch.int64, device="cuda")
 if world > 1:
     dist.barrier()
@@ -45,20 +46,44 @@ if rank != 0:
 t = buf.cpu()
 n = int((t[:, 0] != 0).sum())
 names = {1: "prep", 2: "norm", 3: "gemm", 4: "rope", 5: "attn", 6: "sample", 7: "verify", 8: "misc"}
-ids, ts = t[:n, 0].tolist(), t[:n, 1].tolist()
-print("marks:", n, "step span us:", (ts[-1] - ts[0]) / 1e3)
-# increment attributed to kernel i = time from its dependency-resolved mark to the next kernel's mark
+order = sorted(range(n), key=lambda i: int(t[i, 1]))
+all_ids, all_ts = [int(t[i, 0]) for i in order], [int(t[i, 1]) for i in order]
+# kernel-start marks (id < 16) and the phase marks (id >= 16) that follow each of them
+kern = [i for i in range(n) if all_ids[i] < 16]
+ids, ts = [all_ids[i] for i in kern], [all_ts[i] for i in kern]
+nk = len(ids)
+print("kernels:", nk, "marks:", n, "step span us:", (ts[-1] - ts[0]) / 1e3)
 agg = collections.defaultdict(lambda: [0, 0.0])
-for i in range(n - 1):
+for i in range(nk - 1):
     agg[names[ids[i]]][0] += 1
     agg[names[ids[i]]][1] += (ts[i + 1] - ts[i]) / 1e3
 for k, (c, us) in sorted(agg.items(), key=lambda x: -x[1][1]):
     print(f"{k:8s} n={c:5d} total={us:9.1f} us avg={us / c:6.2f}")
-# one draft layer in detail (skip the first forward's prologue)
-seq = [(names[ids[i]], round((ts[i + 1] - ts[i]) / 1e3, 2)) for i in range(n - 1)]
+seq = [(names[ids[i]], round((ts[i + 1] - ts[i]) / 1e3, 2)) for i in range(nk - 1)]
 print("draft layer sample:", seq[10:20])
 print("target layer sample:", seq[-40:-30])
-# forward boundaries: prep marks
-preps = [i for i in range(n) if ids[i] == 1]
-for a, b in zip(preps, preps[1:] + [n - 1]):
+preps = [i for i in range(nk) if ids[i] == 1]
+for a, b in zip(preps, preps[1:] + [nk - 1]):
     print("forward", (ts[b] - ts[a]) / 1e3, "us", b - a, "kernels")
+
+
+def phases(lo, hi, label):
+    """mean gaps start -> phase marks -> next kernel start, per kernel kind, for kernels lo..hi-1"""
+    acc = collections.defaultdict(lambda: collections.defaultdict(lambda: [0, 0.0]))
+    for j in range(lo, min(hi, nk - 1)):
+        a, b = kern[j], kern[j + 1]
+        pts = [("start", all_ts[a])] + [(f"p{all_ids[i] % 8}", all_ts[i]) for i in range(a + 1, b)] + [("next", all_ts[b])]
+        kind = names[ids[j]]
+        if kind == "attn" and any(40 <= all_ids[i] < 48 for i in range(a + 1, b)):
+            kind = "combine"
+        for (n0, t0), (n1, t1) in zip(pts, pts[1:]):
+            e = acc[kind][f"{n0}->{n1}"]
+            e[0] += 1
+            e[1] += (t1 - t0) / 1e3
+    print(f"--- phase gaps (us), {label}")
+    for kind, d in acc.items():
+        print(f"  {kind:8s} " + "  ".join(f"{k}={v[1] / v[0]:.2f}" for k, v in d.items()))
+
+
+phases(preps[0], preps[1], "first draft forward")
+phases(preps[-1], nk, "target verify forward")
