@@ -46,11 +46,5 @@ def time_shape(H, KV, hd, Q):
     return "  ".join(row)
 
 
-for tq_env in ("", "4", "2", "1"):
-    if tq_env:
-        os.environ["SSDK_ATTN_TQ"] = tq_env  # read by the planner at every call (experiment knob)
-    print("== SSDK_ATTN_TQ =", tq_env or "default", flush=True)
-    for name, H, KV, hd, Q in SHAPES:
-        if tq_env and Q == 1:
-            continue
-        print(f"{name:20s} " + time_shape(H, KV, hd, Q), flush=True)
+for name, H, KV, hd, Q in SHAPES:
+    print(f"{name:20s} " + time_shape(H, KV, hd, Q), flush=True)
