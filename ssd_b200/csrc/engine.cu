@@ -18,6 +18,7 @@
 #include "../../include/ssdk.h"
 #include "attention.cuh"
 #include "common.cuh"
+#include "draft_persistent.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "sampling.cuh"
@@ -269,6 +270,10 @@ struct Workspace {
   RecPart* ver_rec;
   unsigned* ver_counters;
   size_t partial_floats = 0;
+  // persistent draft forward (experimental): inter-phase vectors, split-KV partials, barrier state
+  bf16* dp_vec;
+  float* dp_attn;
+  unsigned* dp_sync;
 };
 
 constexpr int kSampleChunks = 64;
@@ -388,6 +393,9 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.ver_rows = (RowPart*)take((size_t)kVerifyMaxRows * kVerifyCtas * sizeof(RowPart));
   w.ver_rec = (RecPart*)take((size_t)16 * kVerifyCtas * sizeof(RecPart));
   w.ver_counters = (unsigned*)take(64);
+  w.dp_vec = (bf16*)take((size_t)(qmax + 4 * dmax + fmax + 64) * 2);
+  w.dp_attn = (float*)take((size_t)Hmax * kDpSplits * (hdmax + 2) * 4);
+  w.dp_sync = (unsigned*)take(64);
   return (int64_t)align_up(off, 1024);
 }
 
@@ -766,6 +774,83 @@ __global__ void advance_kernel(int32_t* __restrict__ ctx, int64_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // spec step: K+1 draft forwards -> (K+1)-token target forward -> verify      (enqueue only)
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// persistent draft forward (EXPERIMENTAL, SSDK_DRAFT_PERSISTENT=1): one cooperative launch per draft decode forward
+// ------------------------------------------------------------------------------------------
+static bool draft_persistent_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("SSDK_DRAFT_PERSISTENT");
+    v = (s && atoi(s) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+static bool draft_persistent_supported(const Model& m, const Fwd& f) {
+  const int G = m.KV ? m.H / m.KV : 0;
+  return f.B == 1 && f.Q == 1 && m.cfg.tp_size == 1 && m.cfg.layers <= kDpMaxLayers && (m.hd == 64 || m.hd == 128) &&
+         G >= 1 && G <= 8 && m.d % 256 == 0 && m.ffn % 256 == 0 && (m.H * m.hd) % 256 == 0;
+}
+template <int HD, int GMAX>
+static int launch_draft_persistent(Launcher& L, const DpParams& p, size_t smem) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(draft_forward_persistent_kernel<HD, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(num_sms());
+  cfg.blockDim = dim3(kDpThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = L.st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: the phases meet at device-wide barriers
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, draft_forward_persistent_kernel<HD, GMAX>, p);
+  if (err != cudaSuccess) return fail("persistent draft launch failed: %s", cudaGetErrorString(err));
+  L.barrier_op();  // not a PDL primary: the next kernel starts after this grid has drained
+  ++L.count;
+  return 0;
+}
+static int enqueue_draft_persistent(ssdk_engine* e, Launcher& L, const Fwd& f) {
+  Model& m = e->model[SSDK_DRAFT];
+  Workspace& w = e->ws;
+  DpParams p;
+  memset(&p, 0, sizeof(p));
+  p.d = m.d; p.L = m.cfg.layers; p.H = m.H; p.KV = m.KV; p.ffn = m.ffn; p.vocab = m.cfg.vocab; p.qk_norm = m.cfg.qk_norm;
+  p.eps = m.cfg.rms_eps;
+  p.scale_log2 = (1.0f / sqrtf((float)m.hd)) * 1.4426950408889634f;
+  p.embed = m.embed.ptr; p.final_norm = m.final_norm; p.lm_head = m.lm_head.ptr; p.rope = m.rope;
+  p.k_cache = m.k_cache; p.v_cache = m.v_cache;
+  p.cache_layer_stride = (long long)m.num_blocks * e->rt.block_size * m.KV * m.hd;
+  p.block_size = e->rt.block_size; p.max_blocks = e->rt.max_blocks_per_seq;
+  p.token = f.ids; p.ctx0 = f.ctx0; p.pos_offset = f.pos_offset; p.block_table = f.block_tables;
+  bf16* v = w.dp_vec;
+  p.vec_qkv = v; v += align_up((size_t)m.qkv_dim, 8);
+  p.vec_o = v; v += m.d;
+  p.vec_down = v; v += m.d;
+  p.resid0 = v; v += m.d;
+  p.resid1 = v; v += m.d;
+  p.vec_act = v;
+  p.attn_part = w.dp_attn;
+  p.logits = f.logits_mode ? f.logits_out : nullptr;
+  p.bar_counter = w.dp_sync; p.launch_count = w.dp_sync + 1;
+  for (int l = 0; l < p.L; ++l) {
+    const LayerW& lw = m.layers[l];
+    p.layers[l] = DpLayer{lw.qkv.ptr, lw.o.ptr, lw.gate_up.ptr, lw.down.ptr, lw.input_norm, lw.post_norm, lw.q_norm, lw.k_norm};
+  }
+  const int G = m.H / m.KV, gmax = G <= 4 ? 4 : 8;
+  const size_t xs = (size_t)std::max(std::max(m.d, m.ffn), m.H * m.hd);
+  const size_t scratch = (size_t)gmax * m.hd + 2 * m.hd + (size_t)kDpWarps * gmax * (m.hd + 2);
+  const size_t smem = (xs + scratch) * 4;
+  if (m.hd == 64 && gmax == 4) return launch_draft_persistent<64, 4>(L, p, smem);
+  if (m.hd == 64 && gmax == 8) return launch_draft_persistent<64, 8>(L, p, smem);
+  if (m.hd == 128 && gmax == 4) return launch_draft_persistent<128, 4>(L, p, smem);
+  return launch_draft_persistent<128, 8>(L, p, smem);
+}
+
 static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, bool advance) {
   Workspace& w = e->ws;
   const int K = e->rt.spec_k;
@@ -796,7 +881,8 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
     f.logits_mode = (k < K) ? 1 : 0;
     f.logits_out = w.logits_q + (size_t)k * V;
     f.logits_ld = (int64_t)K * V;
-    CKI(enqueue_forward(e, L, f));
+    if (draft_persistent_enabled() && draft_persistent_supported(drf, f)) CKI(enqueue_draft_persistent(e, L, f));
+    else CKI(enqueue_forward(e, L, f));
     if (k < K) {
       SampleParams sp;
       sp.logits = w.logits_q + (size_t)k * V; sp.ld = (int64_t)K * V; sp.temps = tq; sp.V = drf.cfg.vocab;

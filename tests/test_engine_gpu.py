@@ -1,6 +1,8 @@
 """GPU parity of the whole hot path through the C-ABI: prefill -> K+1 draft forwards -> verify forward ->
 accept/reject, driven by ssdk_forward_tokens / ssdk_spec_step, checked step by step against the oracle
 (teacher-forced on the engine's own tokens; decisions with a top-2 logit margin >= EPS must agree exactly)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -184,3 +186,17 @@ def test_resident_mode_matches_host_stepping():
             res.append((total, rec))
         r.close()
     assert res[0] == res[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("SSD_B200_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental persistent draft forward: opt in with SSD_B200_TEST_EXPERIMENTAL=1")
+def test_experimental_persistent_draft_matches_regular_path():
+    """csrc/draft_persistent.cuh is not on the default path; this check is what has to pass before it is."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_draft_persistent.py")], capture_output=True,
+                         text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]

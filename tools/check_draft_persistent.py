@@ -1,0 +1,84 @@
+"""Validate the EXPERIMENTAL persistent draft forward (SSDK_DRAFT_PERSISTENT=1) against the regular kernel-per-op path.
+
+    python tools/check_draft_persistent.py            # runs both modes in subprocesses and compares
+
+Workload: a 2-layer target at Llama-3.1-8B dimensions + the full 16-layer Llama-3.2-1B draft (real draft shapes, synthetic
+bigram-agreement weights), k=6, b=1, greedy.  SD output equals AR output whatever the draft does, so the check is on the
+DRAFT side: the speculated tokens and accept lengths of every step must be identical between the two modes, the draft
+logits of the last step must agree within bf16 GEMV-vs-tensor-core accumulation noise, and the step time is printed."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def worker(out_path):
+    import random
+
+    import numpy as np
+    import torch
+
+    from ssd_b200 import lib as L, synth
+    from ssd_b200.llm import LLM
+
+    root = tempfile.mkdtemp()
+    llm = LLM(synth.make_model_dir(root, "llama-3.1-8b", "target", layers=2), speculate=True,
+              draft=synth.make_model_dir(root, "llama-3.2-1b", "draft"), speculate_k=6, num_gpus=1, max_num_seqs=1,
+              max_model_len=2048, jit_speculate=True)
+    r = llm.runner
+    random.seed(0)
+    prompt = [random.randint(0, 10000) for _ in range(200)]
+    bt = list(range(r.max_blocks))
+    rec = r.prefill(L.TARGET, prompt, bt)
+    r.prefill(L.DRAFT, prompt, bt, want_sample=False)
+    ctx, toks_all, nacc_all = len(prompt), [], []
+    for _ in range(24):
+        toks, nacc, nrec = r.spec_step([ctx], [rec], [bt], [bt], [0.0], [0.0])
+        toks_all.append(toks[0].tolist())
+        nacc_all.append(int(nacc[0]))
+        ctx += int(nacc[0]) + 1
+        rec = int(nrec[0])
+    lq = r.logits_q(1).float().cpu().numpy()
+    r.stage([ctx], [rec], [bt], [bt], [0.0], [0.0])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r.step_resident(4)
+    e0.record()
+    r.step_resident(16)
+    e1.record()
+    torch.cuda.synchronize()
+    np.savez(out_path, toks=np.array(toks_all), nacc=np.array(nacc_all), lq=lq, ms=e0.elapsed_time(e1) / 16)
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--worker":
+        return worker(sys.argv[2])
+    import numpy as np
+
+    res = {}
+    tmp = tempfile.mkdtemp()
+    for mode, env in (("regular", "0"), ("persistent", "1")):
+        out = os.path.join(tmp, mode + ".npz")
+        rc = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", out],
+                            env={**os.environ, "SSDK_DRAFT_PERSISTENT": env}, timeout=600).returncode
+        if rc != 0:
+            sys.exit(f"{mode} run failed (rc={rc})")
+        res[mode] = np.load(out)
+    a, b = res["regular"], res["persistent"]
+    same_tokens = bool((a["toks"] == b["toks"]).all() and (a["nacc"] == b["nacc"]).all())
+    err = float(np.abs(a["lq"] - b["lq"]).max())
+    scale = float(np.abs(a["lq"]).max())
+    report = {"same_speculations_and_accept_lengths": same_tokens, "mean_accept_len": float(a["nacc"].mean() + 1),
+              "draft_logits_max_abs_diff": err, "draft_logits_max_abs": scale,
+              "ms_per_step_regular": float(a["ms"]), "ms_per_step_persistent": float(b["ms"])}
+    print(json.dumps(report))
+    if not same_tokens or err > 0.02 * scale + 0.05:
+        sys.exit("persistent draft forward disagrees with the regular path")
+
+
+if __name__ == "__main__":
+    main()
