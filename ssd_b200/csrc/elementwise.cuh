@@ -176,7 +176,10 @@ SSDK_DEVINL void norm_slice(const NormParams& p, int m, int i, const uint8_t* sy
                             const __nv_bfloat16* erow, bool zero_row, float* x) {
   const int d = p.d;
   uint4 res = make_uint4(0, 0, 0, 0);
-  if (p.residual_in) res = *reinterpret_cast<const uint4*>(p.residual_in + (size_t)m * d + i);
+  // A dataflow (no grid-dependency wait) all-reduce consumer may run while kernels several steps back in the chain are
+  // still executing — with small grids the whole PDL chain is co-resident — so it must not touch `residual` before it has
+  // seen its own rank's flagged words (which imply that the local chain up to the publish kernel has completed).
+  if (p.residual_in && !symm_slots) res = *reinterpret_cast<const uint4*>(p.residual_in + (size_t)m * d + i);
   if (symm_slots) {
     // sum the ranks' bf16 contributions in rank order (identical on every rank), fp32 accumulate, one bf16 rounding.
     // 8 elements = 4 words {2 x bf16, flag} = two 16-byte loads per rank; all ranks' loads are issued before any flag is
@@ -217,6 +220,8 @@ SSDK_DEVINL void norm_slice(const NormParams& p, int m, int i, const uint8_t* sy
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) x[j] = bf16_round(x[j]);
+    asm volatile("" ::: "memory");  // keep the residual load below the polling loop
+    if (p.residual_in) res = *reinterpret_cast<const uint4*>(p.residual_in + (size_t)m * d + i);
   } else if (p.ids) {
     if (zero_row) {
 #pragma unroll
