@@ -151,6 +151,21 @@ SSDK_DEVINL void dp_dot2(const __nv_bfloat16* W, int K, int r0, int r1, const fl
   y1 = warp_sum(b0 + b1);
 }
 
+// Hint only: ask L2 for the first row pair this warp will stream in the NEXT phase, so that HBM keeps working while the
+// CTAs meet at the barrier (units = rows, or gate|up pairs (i, i + pair_offset)).
+SSDK_DEVINL void dp_prefetch_next(const __nv_bfloat16* W, int K, int n_units, int pair_offset) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = warp * gridDim.x + blockIdx.x;
+  if (u0 >= n_units) return;
+  const int second = pair_offset ? u0 + pair_offset : u0 + kDpWarps * (int)gridDim.x;
+  const int rows[2] = {u0, (pair_offset || second < n_units) ? second : u0};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const char* row = reinterpret_cast<const char*>(W + (size_t)rows[k] * K);
+    for (int off = lane * 128; off < K * 2; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+  }
+}
+
 // y[r] = bf16(W[r] . x) for r < n_rows; rows dealt warp-major over the CTAs so every SM streams the same bytes
 SSDK_DEVINL void dp_gemv_rows(const __nv_bfloat16* W, int K, int n_rows, const float* xs, __nv_bfloat16* y) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -424,6 +439,7 @@ __global__ void __launch_bounds__(kDpThreads, 1) draft_forward_persistent_kernel
     }
     cur ^= 1;
     dp_gemv_rows(lw.qkv, p.d, (p.H + 2 * p.KV) * HD, xs, p.vec_qkv);
+    dp_prefetch_next(lw.o, p.H * HD, p.d, 0);
     bar.sync();
     // ---- B: RoPE + KV store + attention units ----
     for (int u = blockIdx.x; u < p.KV * kDpSplits; u += gridDim.x)
@@ -432,11 +448,13 @@ __global__ void __launch_bounds__(kDpThreads, 1) draft_forward_persistent_kernel
     // ---- C: merge splits -> o-proj ----
     dp_combine_prologue<HD>(p, xs);
     dp_gemv_rows(lw.o, p.H * HD, p.d, xs, p.vec_o);
+    dp_prefetch_next(lw.gate_up, p.d, p.ffn, p.ffn);
     bar.sync();
     // ---- D: add + post-attention norm -> gate|up with SiLU*mul ----
     dp_norm_prologue(p.vec_o, resid[cur], resid[cur ^ 1], lw.post_norm, p.eps, p.d, xs, red);
     cur ^= 1;
     dp_gemv_gate_up(lw.gate_up, p.d, p.ffn, xs, p.vec_act);
+    dp_prefetch_next(lw.down, p.ffn, p.d, 0);
     bar.sync();
     // ---- E: down-proj ----
     for (int i = threadIdx.x * 8; i < p.ffn; i += kDpThreads * 8) {
@@ -447,6 +465,8 @@ __global__ void __launch_bounds__(kDpThreads, 1) draft_forward_persistent_kernel
     }
     __syncthreads();
     dp_gemv_rows(lw.down, p.ffn, p.d, xs, p.vec_down);
+    if (l + 1 < p.L) dp_prefetch_next(p.layers[l + 1].qkv, p.d, (p.H + 2 * p.KV) * HD, 0);
+    else if (p.logits) dp_prefetch_next(p.lm_head, p.d, p.vocab, 0);
     bar.sync();
   }
   if (p.logits) {
