@@ -62,6 +62,8 @@ class LLMEngine:
         atexit.register(self.exit)
 
     def exit(self, hard: bool = False):
+        """Tear down TP workers and the runner (llm_engine.py:126-184).  The reference's atexit hook always ends with
+        os._exit(0) to get rid of its helper processes; here that is only done when the caller asks for it (hard=True)."""
         if self._exiting:
             return
         self._exiting = True
@@ -74,6 +76,9 @@ class LLMEngine:
             self.runner.close()
         except Exception:
             pass
+        if hard:
+            import os
+            os._exit(0)
 
     def add_request(self, prompt, sampling_params: SamplingParams):
         if isinstance(prompt, str):
