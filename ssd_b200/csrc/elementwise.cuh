@@ -150,6 +150,11 @@ struct SymmIn {
   unsigned slot_bytes;
 };
 constexpr int kSymmMaxRanks = 8;
+// NOTE (robustness item for the next round): fwd_seq is bumped by prep_kernel at the START of the forward.  A dataflow
+// consumer reads it without a grid-dependency wait, i.e. formally it could run before prep_kernel has finished if the
+// whole PDL chain (>= 9 launches) were co-resident and launched within prep's ~2 us — impossible at model shapes
+// (the GEMM grids serialise the chain) and never observed, but not excluded by construction.  Moving the bump into a
+// one-thread kernel after the forward's last consumer makes it stable long before the next forward starts.
 SSDK_DEVINL unsigned symm_epoch(const unsigned* fwd_seq, int call_idx) { return __ldcg(fwd_seq) * 512u + (unsigned)call_idx + 1u; }
 SSDK_DEVINL size_t symm_slot_off(int call_idx, int rank, unsigned slot_bytes) {
   return ((size_t)(call_idx & 1) * kSymmMaxRanks + rank) * slot_bytes;
