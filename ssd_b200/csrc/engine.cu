@@ -66,8 +66,7 @@ struct Launcher {
 
   template <typename... KArgs, typename... Args>
   int go(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
@@ -575,7 +574,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
            w.positions, w.slot_mapping, w.context_lens,
            (f.which == SSDK_TARGET && tp > 1 && e->symm_n == tp) ? w.ar_state : (unsigned*)nullptr));
 
-  int TQ, MT, nqt, nsplit;
+  int TQ = 1, MT = 1, nqt = 1, nsplit = 1;
   CKI(attn_plan(m, f.B, f.Q, &TQ, &MT, &nqt, &nsplit, e->max_ctx_hint));
   const float scale = 1.0f / sqrtf((float)m.hd);
 
@@ -797,8 +796,7 @@ static int launch_draft_persistent(Launcher& L, const DpParams& p, size_t smem) 
     CK(cudaFuncSetAttribute(draft_forward_persistent_kernel<HD, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(num_sms());
   cfg.blockDim = dim3(kDpThreads);
   cfg.dynamicSmemBytes = smem;
@@ -1014,7 +1012,7 @@ int ssdk_create(const ssdk_model_cfg* target, const ssdk_model_cfg* draft, const
     Model& m = e->model[w];
     m.cfg = *cfgs[w];
     m.present = true;
-    const auto& c = m.cfg;
+    const ssdk_model_cfg c = m.cfg;  // by value: the error paths below free the engine before formatting the message
     if (c.tp_size < 1 || c.heads % c.tp_size || c.kv_heads % c.tp_size || c.ffn % c.tp_size || c.vocab % c.tp_size) {
       delete e;
       return fail("model %d: tp_size %d does not divide heads/kv_heads/ffn/vocab", w, c.tp_size);
@@ -1461,7 +1459,7 @@ int ssdk_sample(const void* logits, int64_t ld, const float* temps, int B, int V
   if (B < 1 || B > kMaxTokens) return fail("sample: B out of range");
   Launcher L;
   L.st = (cudaStream_t)stream;
-  void* scr;
+  void* scr = nullptr;
   CKI(op_scratch(&scr, L.st));
   SampleParams sp;
   sp.logits = (const bf16*)logits; sp.ld = ld; sp.temps = temps; sp.V = V; sp.seed = seed; sp.call_id = step_id;
