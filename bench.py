@@ -316,7 +316,6 @@ def cpu_baseline(tshape, dshape, K, alpha, sample_steps=3, t_layers=2, d_layers=
         return out
 
     # instrument per-model forward time to separate layer time from embedding / head time
-    import oracle.spec as S
     orig_fwd = SpecSession._forward
     def fwd(self, model, ids, ctx0, q_len, btab):
         return timed("t_fwd" if model is t else "d_fwd", lambda: orig_fwd(self, model, ids, ctx0, q_len, btab))

@@ -7,7 +7,6 @@ import atexit
 from dataclasses import fields
 from time import perf_counter
 
-from .. import lib as L
 from ..config import Config
 from ..sampling_params import SamplingParams
 from .scheduler import Scheduler
