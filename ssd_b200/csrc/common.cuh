@@ -1,11 +1,24 @@
 // common.cuh — shared device helpers for the sm_100a kernels of libssdk.
 // PTX wrappers (mbarrier, TMA, tcgen05/TMEM, PDL), bf16 helpers, reductions, Philox.
 #pragma once
+// SSDK_HOST_EMU: the kernels that use no tensor-core / TMA / PTX-only feature can be compiled for the host by the test
+// suite (tests/emu/cuda_emu.h supplies the CUDA vocabulary before this header is included); never defined in the product.
+#ifndef SSDK_HOST_EMU
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#endif
 #include <stdint.h>
 
 #define SSDK_DEVINL __device__ __forceinline__
+
+// shared-memory declarations inside a kernel body
+#ifdef SSDK_HOST_EMU
+#define SSDK_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(::emu::dyn_smem())
+#define SSDK_STATIC_SMEM(T, name, n) T* name = ::emu::static_smem<T>(n, __LINE__)
+#else
+#define SSDK_DYN_SMEM(T, name) extern __shared__ __align__(16) T name[]
+#define SSDK_STATIC_SMEM(T, name, n) __shared__ T name[n]
+#endif
 
 namespace ssdk {
 
@@ -108,6 +121,7 @@ SSDK_DEVINL float u32_to_unit_open0(uint32_t x) {
 // Exp(1) sample from one 32-bit word
 SSDK_DEVINL float u32_to_exp1(uint32_t x) { return -__logf(u32_to_unit_open0(x)); }
 
+#ifndef SSDK_HOST_EMU
 // ----------------------------------------------------------------------------------
 // PTX: shared-address conversion, mbarrier, fences
 // ----------------------------------------------------------------------------------
@@ -289,5 +303,27 @@ SSDK_DEVINL uint4 ld_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+// acquire load at device scope (flag / counter polling)
+SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SSDK_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+#else  // SSDK_HOST_EMU: host stand-ins for the few PTX helpers the emulated kernels use
+enum { TR_PREP = 1, TR_NORM, TR_GEMM, TR_ROPE, TR_ATTN, TR_SAMPLE, TR_VERIFY, TR_MISC };
+enum { TRF_ATTN = 16, TRF_NORM = 24, TRF_ROPE = 32, TRF_COMB = 40, TRF_GEMM = 48 };
+SSDK_DEVINL void trace_mark(int) {}
+SSDK_DEVINL void trace_fine(int) {}
+SSDK_DEVINL void pdl_wait() {}
+SSDK_DEVINL void pdl_launch_dependents() {}
+SSDK_DEVINL uint4 ld_nc_v4(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
+  std::this_thread::yield();
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+}
+SSDK_DEVINL void prefetch_l2(const void*) {}
+#endif
 
 }  // namespace ssdk

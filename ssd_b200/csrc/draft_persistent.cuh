@@ -68,7 +68,7 @@ struct DpGridBar {
       unsigned v;
       const long long t0 = clock64();
       do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        v = ld_acquire_u32(counter);
         if (clock64() - t0 > 4000000000LL) __trap();  // a CTA never arrived: fail loudly instead of hanging the GPU
       } while ((int)(v - target) < 0);
     }
@@ -162,7 +162,7 @@ SSDK_DEVINL void dp_prefetch_next(const __nv_bfloat16* W, int K, int n_units, in
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     const char* row = reinterpret_cast<const char*>(W + (size_t)rows[k] * K);
-    for (int off = lane * 128; off < K * 2; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+    for (int off = lane * 128; off < K * 2; off += 32 * 128) prefetch_l2(row + off);
   }
 }
 
@@ -412,10 +412,10 @@ SSDK_DEVINL void dp_combine_prologue(const DpParams& p, float* xs) {
 
 template <int HD, int GMAX>
 __global__ void __launch_bounds__(kDpThreads, 1) draft_forward_persistent_kernel(const __grid_constant__ DpParams p) {
-  extern __shared__ __align__(16) float dp_smem[];
+  SSDK_DYN_SMEM(float, dp_smem);
   float* xs = dp_smem;                         // [max(d, ffn, H * HD)] fp32 operand vector of the running phase
   float* scratch = xs + max(max(p.d, p.ffn), p.H * HD);  // attention scratch: q, k, v, per-warp partials
-  __shared__ float red[32];
+  SSDK_STATIC_SMEM(float, red, 32);
   if (threadIdx.x == 0) trace_mark(TR_MISC);
 
   DpGridBar bar;

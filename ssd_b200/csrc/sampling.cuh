@@ -25,12 +25,6 @@ SSDK_DEVINL uint32_t u4_word(const uint4& v, int w) { return w == 0 ? v.x : (w =
 // uniform in [0,1) like torch.rand
 SSDK_DEVINL float u32_to_unit_half_open(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // block-wide argmax (blockDim.x <= 1024); result valid in thread 0
 SSDK_DEVINL ArgMax block_argmax(ArgMax a, ArgMax* red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
