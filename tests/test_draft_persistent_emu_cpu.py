@@ -18,6 +18,11 @@ SRC = os.path.join(ROOT, "tests", "emu", "run_draft_persistent.cpp")
 BIN = os.path.join(ROOT, "tests", "emu", "_build", "run_draft_persistent")
 
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20)")
+# SSD_B200_TSAN=1: build the emulated kernel with -fsanitize=thread; any unsynchronised conflicting access to "shared" or
+# "global" memory (a missing __syncthreads, a vector read before the device-wide barrier) is then reported as a data race.
+TSAN = os.environ.get("SSD_B200_TSAN") == "1"
+if TSAN:
+    BIN += "_tsan"
 
 
 def _build():
@@ -26,7 +31,9 @@ def _build():
     if os.path.exists(BIN) and all(os.path.getmtime(BIN) >= os.path.getmtime(d) for d in deps):
         return
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
-    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-Wno-attributes", "-o", BIN, SRC], check=True)
+    flags = ["-fsanitize=thread", "-g"] if TSAN else []
+    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-Wno-attributes", *flags, "-o", BIN, SRC],
+                   check=True)
 
 
 def _u16(t):
@@ -81,8 +88,9 @@ def test_persistent_draft_kernel_source_on_host_threads(tmp_path, family, grid):
         _u16(kv0[0]).tofile(f)  # [L, nblk, bs, KV, hd] == [L, slots, KV, hd]
         _u16(kv0[1]).tofile(f)
     out = tmp_path / "out.bin"
-    res = subprocess.run([BIN, str(blob), str(out)], capture_output=True, text=True, timeout=900)
+    res = subprocess.run([BIN, str(blob), str(out)], capture_output=True, text=True, timeout=3000)
     assert res.returncode == 0, res.stderr[-2000:]
+    assert "ThreadSanitizer" not in res.stderr, res.stderr[:3000]
     raw = np.fromfile(out, dtype=np.uint16)
     nl = 3 * cfg.vocab
     got = torch.from_numpy(raw[:nl].astype(np.int16)).view(torch.bfloat16).float().numpy().reshape(3, cfg.vocab)
