@@ -15,9 +15,11 @@
 #ifdef SSDK_HOST_EMU
 #define SSDK_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(::emu::dyn_smem())
 #define SSDK_STATIC_SMEM(T, name, n) T* name = ::emu::static_smem<T>(n, __LINE__)
+#define SSDK_SHARED_VAR(T, name) T& name = *::emu::static_smem<T>(1, __LINE__)
 #else
 #define SSDK_DYN_SMEM(T, name) extern __shared__ __align__(16) T name[]
 #define SSDK_STATIC_SMEM(T, name, n) __shared__ T name[n]
+#define SSDK_SHARED_VAR(T, name) __shared__ T name
 #endif
 
 namespace ssdk {

@@ -57,8 +57,8 @@ struct SampleParams {
 };
 
 __global__ void __launch_bounds__(256) sample_kernel(SampleParams p) {
-  __shared__ ArgMax red[32];
-  __shared__ bool is_last;
+  SSDK_STATIC_SMEM(ArgMax, red, 32);
+  SSDK_SHARED_VAR(bool, is_last);
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(TR_SAMPLE);
@@ -175,13 +175,16 @@ SSDK_DEVINL void online_merge(float& m, float& s, float m2, float s2) {
 }
 
 __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(VerifyParams p) {
-  __shared__ ArgMax red[32];
-  __shared__ float redm[4], reds[4];
-  __shared__ int row_arg[kVerifyMaxRows];
-  __shared__ float row_m[kVerifyMaxRows], row_z[kVerifyMaxRows];
-  __shared__ int s_n[16], s_flags[16];      // accepted count; bit0 = needs recovery draw, bit1 = adjust
-  __shared__ long long s_rec_greedy[16];
-  __shared__ bool is_last;
+  SSDK_STATIC_SMEM(ArgMax, red, 32);
+  SSDK_STATIC_SMEM(float, redm, 4);
+  SSDK_STATIC_SMEM(float, reds, 4);
+  SSDK_STATIC_SMEM(int, row_arg, kVerifyMaxRows);
+  SSDK_STATIC_SMEM(float, row_m, kVerifyMaxRows);
+  SSDK_STATIC_SMEM(float, row_z, kVerifyMaxRows);
+  SSDK_STATIC_SMEM(int, s_n, 16);      // accepted count
+  SSDK_STATIC_SMEM(int, s_flags, 16);  // bit0 = needs recovery draw, bit1 = adjust
+  SSDK_STATIC_SMEM(long long, s_rec_greedy, 16);
+  SSDK_SHARED_VAR(bool, is_last);
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(TR_VERIFY);

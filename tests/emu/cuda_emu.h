@@ -127,27 +127,41 @@ template <typename T>
 inline T __ldcg(const T* p) { return *p; }
 
 namespace emu {
-// run kernel(params) on grid x block host threads (1-D grid and block)
+// run kernel(params) on grid.x * grid.y CTAs of `block` host threads each.  `wave` > 0 runs the CTAs in batches of that
+// size (only valid for kernels whose CTAs never wait for one another: ticket / last-block patterns are fine, device-wide
+// barriers are not); wave == 0 makes every CTA co-resident.
 template <typename Kernel, typename Params>
-void launch(Kernel kernel, const Params& params, int grid, int block, size_t dyn_smem_bytes) {
+void launch(Kernel kernel, const Params& params, dim3 grid, int block, size_t dyn_smem_bytes, int wave = 0) {
   if (block % 32) {
     std::fprintf(stderr, "[cuda_emu] block size must be a multiple of 32\n");
     std::abort();
   }
-  std::vector<std::unique_ptr<Cta>> ctas;
-  for (int b = 0; b < grid; ++b) ctas.push_back(std::make_unique<Cta>(block, dyn_smem_bytes));
-  std::vector<std::thread> ts;
-  ts.reserve((size_t)grid * block);
-  for (int b = 0; b < grid; ++b)
-    for (int t = 0; t < block; ++t)
-      ts.emplace_back([&, b, t] {
-        tctx.cta = ctas[b].get();
-        threadIdx.x = t;
-        blockIdx.x = b;
-        blockDim.x = block;
-        gridDim.x = grid;
-        kernel(params);
-      });
-  for (auto& t : ts) t.join();
+  const int total = (int)(grid.x * grid.y);
+  if (wave <= 0) wave = total;
+  for (int first = 0; first < total; first += wave) {
+    const int n = std::min(wave, total - first);
+    std::vector<std::unique_ptr<Cta>> ctas;
+    for (int b = 0; b < n; ++b) ctas.push_back(std::make_unique<Cta>(block, dyn_smem_bytes));
+    std::vector<std::thread> ts;
+    ts.reserve((size_t)n * block);
+    for (int b = 0; b < n; ++b)
+      for (int t = 0; t < block; ++t)
+        ts.emplace_back([&, b, t] {
+          tctx.cta = ctas[b].get();
+          threadIdx.x = t;
+          blockIdx.x = (unsigned)(first + b) % grid.x;
+          blockIdx.y = (unsigned)(first + b) / grid.x;
+          blockDim.x = block;
+          gridDim = grid;
+          kernel(params);
+        });
+    for (auto& t : ts) t.join();
+  }
+}
+template <typename Kernel, typename Params>
+void launch(Kernel kernel, const Params& params, int grid, int block, size_t dyn_smem_bytes) {
+  dim3 g;
+  g.x = (unsigned)grid;
+  launch(kernel, params, g, block, dyn_smem_bytes, 0);
 }
 }  // namespace emu
