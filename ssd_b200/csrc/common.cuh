@@ -312,6 +312,12 @@ SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 SSDK_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 16-byte volatile load (flag-in-word polling: re-issued on every call, never cached in registers)
+SSDK_DEVINL uint4 ld_volatile_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 
 #else  // SSDK_HOST_EMU: host stand-ins for the few PTX helpers the emulated kernels use
 enum { TR_PREP = 1, TR_NORM, TR_GEMM, TR_ROPE, TR_ATTN, TR_SAMPLE, TR_VERIFY, TR_MISC };
@@ -326,6 +332,13 @@ SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 }
 SSDK_DEVINL void prefetch_l2(const void*) {}
+SSDK_DEVINL uint4 ld_volatile_v4(const void* p) {
+  // two aligned 8-byte words {2 x bf16, epoch}: each is read atomically, like the device's 8-byte store granularity
+  const uint64_t* q = reinterpret_cast<const uint64_t*>(p);
+  const uint64_t a = __atomic_load_n(q, __ATOMIC_ACQUIRE), b = __atomic_load_n(q + 1, __ATOMIC_ACQUIRE);
+  std::this_thread::yield();
+  return make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+}
 #endif
 
 }  // namespace ssdk

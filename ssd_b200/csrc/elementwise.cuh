@@ -200,8 +200,8 @@ SSDK_DEVINL void norm_slice(const NormParams& p, int m, int i, const uint8_t* sy
       for (int r = 0; r < kSymmMaxRanks; ++r) {
         if (r < p.symm.n_ranks) {
           const uint4* src = reinterpret_cast<const uint4*>(symm_slots + (size_t)r * p.symm.slot_bytes) + word0 / 2;
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo[r].x), "=r"(lo[r].y), "=r"(lo[r].z), "=r"(lo[r].w) : "l"(src));
-          asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi[r].x), "=r"(hi[r].y), "=r"(hi[r].z), "=r"(hi[r].w) : "l"(src + 1));
+          lo[r] = ld_volatile_v4(src);
+          hi[r] = ld_volatile_v4(src + 1);
         }
       }
       ready = true;
@@ -253,8 +253,8 @@ SSDK_DEVINL void norm_slice(const NormParams& p, int m, int i, const uint8_t* sy
 // one round trip per slab, 3-4 us per call.)
 template <int SLICES>
 __global__ void __launch_bounds__(512) add_rmsnorm_kernel(NormParams p) {
-  extern __shared__ float rbuf[];  // d floats (SLICES == 0 only)
-  __shared__ float red[32];
+  SSDK_DYN_SMEM(float, rbuf);  // d floats (SLICES == 0 only)
+  SSDK_STATIC_SMEM(float, red, 32);
   pdl_launch_dependents();
   // All-reduce consumers after a row-parallel GEMM are pure dataflow: every input word (including THIS rank's own
   // contribution) carries the epoch flag, so the kernel does not have to wait for the publishing kernel to *complete*

@@ -1,0 +1,82 @@
+"""The one-shot all-reduce of the tensor-parallel path — `ar_publish_kernel` + the flag-polling input of
+`add_rmsnorm_kernel` (csrc/elementwise.cuh) — executed from SOURCE for 2 and 8 emulated ranks that share host memory the
+way peer-mapped symmetric buffers share HBM (tests/emu/run_allreduce.cpp).  Ranks are skewed against each other with
+random delays, five consecutive all-reduces reuse the two parity slots, and every rank must produce
+bf16( sum over ranks, in rank order, of that rank's bf16-rounded split-K reduction ) -> residual add -> RMSNorm,
+bit-identically on all ranks.  Covers the 1-slice and the 2-slice norm instantiations."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emu", "run_allreduce.cpp")
+BIN = os.path.join(ROOT, "tests", "emu", "_build", "run_allreduce")
+BF = torch.bfloat16
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (C++20)")
+
+
+def _build():
+    deps = [SRC, os.path.join(ROOT, "tests", "emu", "cuda_emu.h"), os.path.join(ROOT, "ssd_b200", "csrc", "elementwise.cuh"),
+            os.path.join(ROOT, "ssd_b200", "csrc", "common.cuh")]
+    if os.path.exists(BIN) and all(os.path.getmtime(BIN) >= os.path.getmtime(d) for d in deps):
+        return
+    os.makedirs(os.path.dirname(BIN), exist_ok=True)
+    subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-Wno-unknown-pragmas", "-Wno-attributes", "-o", BIN, SRC], check=True)
+
+
+def _u16(t):
+    return t.contiguous().view(torch.int16).numpy().astype(np.uint16)
+
+
+@pytest.mark.parametrize("R,M,d,S,threads", [(8, 3, 512, 3, 64), (2, 2, 8192, 4, 512)])
+def test_one_shot_allreduce_source_on_emulated_ranks(tmp_path, R, M, d, S, threads):
+    _build()
+    g = torch.Generator().manual_seed(R * 1000 + d)
+    n_calls, eps = 5, 1e-5
+    w = (1.0 + 0.1 * torch.randn(d, generator=g)).to(BF)
+    resid = torch.randn(M, d, generator=g).to(BF)
+    partials = torch.randn(R, n_calls, S, M, d, generator=g) * 0.5
+    inp, out = tmp_path / "ar.in", tmp_path / "ar.out"
+    with open(inp, "wb") as f:
+        np.array([R, M, d, S, n_calls, threads], dtype=np.int32).tofile(f)
+        np.array([eps], dtype=np.float32).tofile(f)
+        _u16(w).tofile(f)
+        _u16(resid).tofile(f)
+        for r in range(R):
+            partials[r].numpy().astype(np.float32).tofile(f)
+    res = subprocess.run([BIN, str(inp), str(out)], capture_output=True, text=True, timeout=1800)
+    assert res.returncode == 0, res.stderr[-2000:]
+    raw = np.fromfile(out, dtype=np.uint16)
+    per = n_calls * M * d + M * d
+    # expectation: each rank publishes bf16(sum_s partial) (s in order, fp32); the consumer sums ranks in rank order in
+    # fp32 and rounds once; then r = x + residual (fp32), residual' = bf16(r), y = bf16(r * rstd * w)
+    res_exp = resid.float()
+    ys = []
+    for c in range(n_calls):
+        acc = torch.zeros(M, d)
+        for r in range(R):
+            contrib = torch.zeros(M, d)
+            for s in range(S):
+                contrib = contrib + partials[r, c, s]
+            acc = acc + contrib.to(BF).float()
+        x = acc.to(BF).float()
+        rr = x + res_exp
+        res_exp = rr.to(BF).float()
+        rstd = torch.rsqrt((rr * rr).mean(-1, keepdim=True) + eps)
+        ys.append((rr * rstd * w.float()).to(BF))
+    want_y = torch.stack(ys)
+    for r in range(R):
+        blk = raw[r * per:(r + 1) * per]
+        y = torch.from_numpy(blk[:n_calls * M * d].astype(np.int16)).view(BF).reshape(n_calls, M, d)
+        rs = torch.from_numpy(blk[n_calls * M * d:].astype(np.int16)).view(BF).reshape(M, d)
+        assert torch.equal(rs, res_exp.to(BF)), f"rank {r}: residual differs"
+        mism = (y.view(torch.int16) != want_y.view(torch.int16)).float().mean().item()
+        assert mism < 2e-3, f"rank {r}: {mism:.2e} of the outputs differ"  # rsqrt / reduction-order ulps only
+        if r:
+            first = torch.from_numpy(raw[:n_calls * M * d].astype(np.int16)).view(BF)
+            assert torch.equal(y.reshape(-1), first), "ranks disagree bit-wise"
