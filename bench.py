@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — decode tokens/s of the sync speculative-decoding hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 70b|8b|qwen32b|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu]
+                    [--workload 70b|8b|qwen32b|tiny] [--temp T] [--lm-scale S]
 
 A "step" is one pass of the hot path over one batch: K_spec+1 draft forwards -> one (K_spec+1)-token target
 forward -> accept/reject+resample.  Workload (N=1 default): Llama-3.1-70B target + Llama-3.2-1B draft, k=6, b=1,
@@ -14,6 +15,12 @@ temp 0, synthetic "bigram agreement" weights at the exact shapes (there are no c
   roofline  achieved HBM GB/s of the dominant kernel (weight-streaming tcgen05 GEMM, largest instance) vs the
             measured peak, plus the whole-step fraction of the HBM roofline of SURVEY §8(d)
   cpu_baseline  the oracle (CPU restatement of the reference path) timed on the host cores on a bounded sample
+  parity_check  temp 0: the tokens of the timed device-resident loop AND of the engine (e2e) loop against the closed-form
+            greedy chain of the synthetic target (t_{i+1} = pi_t(t_i)) — token-for-token, at every N
+  allreduce "symm" (one-shot NVLink all-reduce, ssd_b200's own kernels) | "nccl" (SSD_B200_NO_SYMM=1) | "none" (N=1)
+  reference_gpu  (N=1) the UNMODIFIED reference engine on this box's GPU (baseline/ref_gpu.py: torch.compile, cuBLAS,
+            its CUDA graphs, flash_attn 2.8.3 stub) on the same weights and prompt: its tokens/s, and whether its tokens
+            equal ours; `--impl reference-gpu` prints that arm alone
 """
 from __future__ import annotations
 
@@ -89,6 +96,45 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+def usable_cores() -> int:
+    """Threads the CPU arm may really use: min(CPU affinity, cgroup cpu.max quota).  os.cpu_count() reports the host's
+    128 logical CPUs while the container's quota is 16 — 128 oversubscribed threads made the round-1 CPU arm swing 13x."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def run_reference_gpu_subprocess(args, timeout_s: int = 900):
+    """bench.py --impl reference-gpu / the `reference_gpu` object of the default line: baseline/ref_gpu.py in its own
+    process (the reference calls os._exit from an atexit hook, and both engines cannot hold a 70B model at once)."""
+    out_path = os.path.join(tempfile.mkdtemp(prefix="ssd_refgpu_"), "ref.json")
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_gpu.py"), "--workload", args.workload, "--steps", str(args.steps),
+           "--warmup", str(args.warmup), "--spec-k", str(args.spec_k), "--alpha", str(args.alpha), "--prompt-len",
+           str(args.prompt_len), "--temp", str(args.temp), "--out", out_path]
+    if args.lm_scale:
+        cmd += ["--lm-scale", str(args.lm_scale)]
+    t0 = time.time()
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+        with open(out_path) as f:
+            d = json.loads(f.read())
+    except Exception as exc:  # noqa: BLE001
+        tail = ""
+        try:
+            tail = (res.stdout + res.stderr)[-300:]
+        except Exception:
+            pass
+        d = {"impl": "reference-gpu", "unavailable": f"{type(exc).__name__}: {exc} {tail}"[:500]}
+    d["wall_s"] = round(time.time() - t0, 1)
+    return d
+
+
 def bytes_per_step(tshape, dshape, K, ctx, tp):
     """(K+1)(W_draft + ctx*kv_d) + (W_target + ctx*kv_t)/TP + (2K+1)*V*2."""
     V = 151936 if "qwen" in tshape else 128256
@@ -121,8 +167,12 @@ def run_ours(args):
     root = tempfile.mkdtemp(prefix="ssd_b200_bench_")
     need = args.prompt_len + (args.steps + max(args.warmup, 3) + 6) * (K + 1) + 64
     max_len = max(4096, -(-need // 256) * 256)
-    tdir = synth.make_model_dir(root, tshape, "target", seed=0, alpha=args.alpha)
-    ddir = synth.make_model_dir(root, dshape, "draft", seed=0, alpha=args.alpha)
+    ref_gpu = None
+    if world == 1 and not args.no_ref_gpu and args.workload != "tiny":
+        ref_gpu = run_reference_gpu_subprocess(args)  # BEFORE our engine takes the GPU memory (70B: 141 GB each)
+    tdir = synth.make_model_dir(root, tshape, "target", seed=0, alpha=args.alpha, lm_scale=args.lm_scale)
+    ddir = synth.make_model_dir(root, dshape, "draft", seed=0, alpha=args.alpha, lm_scale=args.lm_scale)
+    temp = float(args.temp)
     t_init = time.time()
     llm = LLM(tdir, speculate=True, draft=ddir, speculate_k=K, num_gpus=world, max_num_seqs=1, max_model_len=max_len,
               kvcache_block_size=256, jit_speculate=True, enforce_eager=False, use_pdl=not args.no_pdl, verbose=False)
@@ -130,7 +180,7 @@ def run_ours(args):
     runner = llm.runner
     import random
     random.seed(0)
-    prompt = [random.randint(0, 10000) for _ in range(args.prompt_len)]
+    prompt = [random.randint(0, 10000) % synth.SHAPES[tshape][6] for _ in range(args.prompt_len)]
     steps, warm = args.steps, args.warmup
     budget_tokens = (steps + warm + 4) * (K + 1) + 8
 
@@ -145,7 +195,7 @@ def run_ours(args):
     bt = list(range(nblk))
     rec = runner.prefill(L.TARGET, prompt, bt)
     runner.prefill(L.DRAFT, prompt, bt, want_sample=False)
-    runner.stage([len(prompt)], [rec], [bt], [bt], [0.0], [0.0])
+    runner.stage([len(prompt)], [rec], [bt], [bt], [temp], [temp])
     for _ in range(warm):
         runner.step_resident(1)
     sync_all()
@@ -161,6 +211,7 @@ def run_ours(args):
         sync_all()
     ms_dev = e0.elapsed_time(e1)
     _, tot1, _ = runner.fetch(1)
+    dev_log = runner.resident_log(0)
     launches = runner.launch_count - l0
     toks_dev = int(tot1[0] - tot0[0])
     if world > 1:
@@ -173,7 +224,8 @@ def run_ours(args):
     # ---------------- end to end: public engine API, host buffers every step ----------------
     e2e = None
     if rank == 0 or world > 1:
-        llm.add_request(prompt, SamplingParams(temperature=0.0, max_new_tokens=budget_tokens, ignore_eos=True))
+        llm.add_request(prompt, SamplingParams(temperature=temp, max_new_tokens=budget_tokens, ignore_eos=True))
+        e2e_seq = llm.scheduler.waiting[-1]
         step = llm.create_inference_step(llm.config)
         for k in llm_engine.METRICS:
             llm_engine.METRICS[k] = [] if isinstance(llm_engine.METRICS[k], list) else 0
@@ -192,6 +244,7 @@ def run_ours(args):
         e2e = {"value": toks / dt, "unit": "tokens/s", "h2d_bytes_per_step": int(runner.step_io_bytes()[0]),
                "d2h_bytes_per_step": int(runner.step_io_bytes()[1]), "ms_per_step": dt / steps * 1e3,
                "accept_len": sum(lens) / max(1, len(lens))}
+        e2e_tokens = list(e2e_seq.completion_token_ids)
 
     if rank != 0:
         if world > 1:
@@ -201,6 +254,36 @@ def run_ours(args):
             except Exception:
                 pass
         return
+    # ---------------- parity: the generated tokens against the closed-form greedy chain of the synthetic target ----------------
+    parity = None
+    if temp == 0.0 and not args.lm_scale:
+        pi_t, _ = synth.permutations(synth.SHAPES[tshape][6], 0, args.alpha, "cpu")
+        pi_t = pi_t.tolist()
+
+        def chain_mismatches(first_prev, toks_):
+            bad, prev = 0, first_prev
+            for t in toks_:
+                bad += int(t != pi_t[prev])
+                prev = t
+            return bad
+
+        # resident log: first entry = the recovery token sampled by the prefill = pi_t(last prompt token)
+        m_dev = chain_mismatches(prompt[-1], dev_log)
+        m_e2e = chain_mismatches(prompt[-1], e2e_tokens)
+        parity = {"tokens": len(dev_log) + len(e2e_tokens), "mismatches": m_dev + m_e2e,
+                  "device_loop": {"tokens": len(dev_log), "mismatches": m_dev},
+                  "engine_loop": {"tokens": len(e2e_tokens), "mismatches": m_e2e},
+                  "against": "t[i+1] == pi_target(t[i]) from the last prompt token (greedy chain of the synthetic target)"}
+        if ref_gpu and ref_gpu.get("tokens"):
+            n = min(len(ref_gpu["tokens"]), len(e2e_tokens))
+            ref_gpu["tokens_compared_with_ours"] = n
+            ref_gpu["token_mismatches_vs_ours"] = sum(int(a != b) for a, b in zip(ref_gpu["tokens"][:n], e2e_tokens[:n]))
+        if parity["mismatches"]:
+            print(f"[bench] PARITY FAILURE: {parity}", file=sys.stderr, flush=True)
+    if ref_gpu is not None:
+        ref_gpu.pop("tokens", None)
+        if "value" in ref_gpu and e2e:
+            ref_gpu["ours_e2e_over_reference_gpu"] = e2e["value"] / ref_gpu["value"]
     # ---------------- roofline ----------------
     peak, peak_src = measured_peaks()
     accept_len = toks_dev / steps
@@ -216,13 +299,19 @@ def run_ours(args):
         "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_dev / steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "accept_len": accept_len,
-        "config": {"workload": f"{desc}, sync SD k={K} b=1 temp=0, TP={world}, prompt {args.prompt_len} random tokens, "
+        "config": {"workload": f"{desc}, sync SD k={K} b=1 temp={temp:g}, TP={world}, prompt {args.prompt_len} random tokens, "
                                f"synthetic bigram-agreement weights alpha={args.alpha} (expected accept-len "
                                f"{synth.expected_tokens_per_step(args.alpha, K):.2f})",
                    "l2": "inputs larger than L2: every step streams the full weight set (>= 2.4 GB) through HBM",
                    "init_s": round(init_s, 1)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "parity_check": parity,
+        "allreduce": ("none" if world == 1 else ("symm" if getattr(runner, "symm", False) else "nccl")),
+        "draft_path": os.environ.get("SSDK_DRAFT_PERSISTENT", "default"),
+        "reference_gpu": ref_gpu,
     }
+    if args.lm_scale:
+        out["config"]["lm_scale"] = args.lm_scale
     print(json.dumps(out), flush=True)
     if world > 1:
         try:
@@ -298,7 +387,7 @@ def cpu_baseline(tshape, dshape, K, alpha, sample_steps=3, t_layers=2, d_layers=
             w["layers"].append(lw)
         return w
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     tc, tL = cfg(tshape, t_layers)
     dc, dL = cfg(dshape, d_layers)
@@ -363,7 +452,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=6)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--temp", type=float, default=0.0, help="sampling temperature of target and draft (BASELINE config 4: 0.7)")
+    ap.add_argument("--lm-scale", type=float, default=None, help="synthetic lm_head scale (softens the distribution for temp>0)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference GPU arm inside the default line")
     ap.add_argument("--workload", default="70b", choices=sorted(WORKLOADS))
     ap.add_argument("--spec-k", type=int, default=6)
     ap.add_argument("--alpha", type=float, default=0.85)
@@ -374,6 +466,9 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps(run_reference_gpu_subprocess(args)), flush=True)
     else:
         run_ours(args)
 

@@ -156,6 +156,11 @@ int ssdk_spec_step_stage(ssdk_handle h, int batch,
 int ssdk_spec_step_resident(ssdk_handle h, int batch, void* stream);
 int ssdk_spec_step_fetch(ssdk_handle h, int batch, int64_t* out_tokens,
                          int32_t* out_n_accept, int64_t* out_recovery, void* stream);
+/* Resident mode: copy the tokens sequence `seq` has emitted since ssdk_spec_step_stage (each step's recovery token +
+ * accepted draft tokens, i.e. what Scheduler.postprocess_speculate appends, engine/scheduler.py:285-327) into
+ * out_tokens[0 .. cap).  Returns the number of tokens copied (>= 0) or < 0 on error.  The device keeps at most
+ * 16384 tokens per sequence. */
+int ssdk_spec_step_log(ssdk_handle h, int seq, int64_t* out_tokens, int cap, void* stream);
 
 /* Generic multi-token forward + sample of the last position of every sequence.
  * Replaces ModelRunner.run for prefill chunks (q_len<=64 per call, causal over the

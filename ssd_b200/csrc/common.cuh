@@ -305,6 +305,15 @@ SSDK_DEVINL uint4 ld_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+// the same with an L2 evict-first hint: a weight line that has been consumed is the first candidate for replacement, so
+// lines prefetched for LATER phases (cp.async.bulk.prefetch.L2) survive in L2 until they are read
+SSDK_DEVINL uint4 ld_nc_v4_evict_first(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(kEvictFirst));
+  return r;
+}
 // acquire load at device scope (flag / counter polling)
 SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -327,6 +336,7 @@ SSDK_DEVINL void trace_fine(int) {}
 SSDK_DEVINL void pdl_wait() {}
 SSDK_DEVINL void pdl_launch_dependents() {}
 SSDK_DEVINL uint4 ld_nc_v4(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+SSDK_DEVINL uint4 ld_nc_v4_evict_first(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
   std::this_thread::yield();
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);

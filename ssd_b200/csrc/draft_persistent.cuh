@@ -134,8 +134,8 @@ SSDK_DEVINL void dp_dot2(const __nv_bfloat16* W, int K, int r0, int r1, const fl
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const bool in = j0 + u < steps;
-      w0[u] = in ? ld_nc_v4(p0 + (size_t)(j0 + u) * 32) : make_uint4(0, 0, 0, 0);
-      w1[u] = (in && r1 >= 0) ? ld_nc_v4(p1 + (size_t)(j0 + u) * 32) : make_uint4(0, 0, 0, 0);
+      w0[u] = in ? ld_nc_v4_evict_first(p0 + (size_t)(j0 + u) * 32) : make_uint4(0, 0, 0, 0);
+      w1[u] = (in && r1 >= 0) ? ld_nc_v4_evict_first(p1 + (size_t)(j0 + u) * 32) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -151,18 +151,27 @@ SSDK_DEVINL void dp_dot2(const __nv_bfloat16* W, int K, int r0, int r1, const fl
   y1 = warp_sum(b0 + b1);
 }
 
-// Hint only: ask L2 for the first row pair this warp will stream in the NEXT phase, so that HBM keeps working while the
-// CTAs meet at the barrier (units = rows, or gate|up pairs (i, i + pair_offset)).
-SSDK_DEVINL void dp_prefetch_next(const __nv_bfloat16* W, int K, int n_units, int pair_offset) {
+// The weights do not depend on the activations, so HBM need not idle while the CTAs meet at a barrier or run a
+// phase prologue: at the START of a phase every warp asks L2 (cp.async.bulk.prefetch.L2 — fire and forget, no data
+// returns to the SM) for all the weight rows it will consume in a LATER phase.  The GEMV of that phase then streams from
+// L2 while HBM is already fetching the phase after it; 126 MB of L2 hold more than a whole 1B layer (121 MB).
+// Units = rows, or gate|up pairs (i, i + pair_offset), dealt like dp_gemv_rows / dp_gemv_gate_up deal them:
+// unit = warp * #CTAs + CTA + j * #warps.
+SSDK_DEVINL void dp_bulk_prefetch_l2(const void* p, uint32_t bytes) {
+#ifndef SSDK_HOST_EMU
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+  (void)p; (void)bytes;
+#endif
+}
+SSDK_DEVINL void dp_prefetch_next(const __nv_bfloat16* W, int K, int n_units, int pair_offset, int max_units_per_warp = 32) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int u0 = warp * gridDim.x + blockIdx.x;
-  if (u0 >= n_units) return;
-  const int second = pair_offset ? u0 + pair_offset : u0 + kDpWarps * (int)gridDim.x;
-  const int rows[2] = {u0, (pair_offset || second < n_units) ? second : u0};
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const char* row = reinterpret_cast<const char*>(W + (size_t)rows[k] * K);
-    for (int off = lane * 128; off < K * 2; off += 32 * 128) prefetch_l2(row + off);
+  if (lane != 0) return;  // the instruction takes warp-uniform operands: one lane issues the warp's whole list
+  const int nw = kDpWarps * (int)gridDim.x;
+  int u = warp * (int)gridDim.x + (int)blockIdx.x;
+  for (int j = 0; j < max_units_per_warp && u < n_units; ++j, u += nw) {
+    dp_bulk_prefetch_l2(W + (size_t)u * K, (uint32_t)K * 2u);
+    if (pair_offset) dp_bulk_prefetch_l2(W + (size_t)(u + pair_offset) * K, (uint32_t)K * 2u);
   }
 }
 
@@ -428,9 +437,13 @@ __global__ void __launch_bounds__(kDpThreads, 1) draft_forward_persistent_kernel
   __nv_bfloat16* resid[2] = {p.resid0, p.resid1};
   int cur = 0;  // resid[cur] holds the residual entering the layer (layer 0: the embedding row itself)
 
+  const int qkv_rows = (p.H + 2 * p.KV) * HD;
+  dp_prefetch_next(p.layers[0].qkv, p.d, qkv_rows, 0);
+  dp_prefetch_next(p.layers[0].o, p.H * HD, p.d, 0);
   for (int l = 0; l < p.L; ++l) {
     const DpLayer& lw = p.layers[l];
-    // ---- A: (add +) input norm -> q|k|v ----
+    // ---- A: (add +) input norm -> q|k|v ----      (HBM meanwhile: this layer's gate|up, 55 % of the layer's bytes)
+    dp_prefetch_next(lw.gate_up, p.d, p.ffn, p.ffn);
     if (l == 0) {
       // first layer: hidden = norm(embed), residual = embed (models/llama3.py:192-193)
       dp_norm_prologue(emb, nullptr, resid[cur ^ 1], lw.in_norm, p.eps, p.d, xs, red);
@@ -438,23 +451,27 @@ __global__ void __launch_bounds__(kDpThreads, 1) draft_forward_persistent_kernel
       dp_norm_prologue(p.vec_down, resid[cur], resid[cur ^ 1], lw.in_norm, p.eps, p.d, xs, red);
     }
     cur ^= 1;
-    dp_gemv_rows(lw.qkv, p.d, (p.H + 2 * p.KV) * HD, xs, p.vec_qkv);
-    dp_prefetch_next(lw.o, p.H * HD, p.d, 0);
+    dp_gemv_rows(lw.qkv, p.d, qkv_rows, xs, p.vec_qkv);
     bar.sync();
     // ---- B: RoPE + KV store + attention units ----
     for (int u = blockIdx.x; u < p.KV * kDpSplits; u += gridDim.x)
       dp_attention_unit<HD, GMAX>(p, l, u / kDpSplits, u % kDpSplits, ctx, scratch);
     bar.sync();
-    // ---- C: merge splits -> o-proj ----
+    // ---- C: merge splits -> o-proj ----            (HBM meanwhile: this layer's down-proj)
+    dp_prefetch_next(lw.down, p.ffn, p.d, 0);
     dp_combine_prologue<HD>(p, xs);
     dp_gemv_rows(lw.o, p.H * HD, p.d, xs, p.vec_o);
-    dp_prefetch_next(lw.gate_up, p.d, p.ffn, p.ffn);
     bar.sync();
-    // ---- D: add + post-attention norm -> gate|up with SiLU*mul ----
+    // ---- D: add + post-attention norm -> gate|up with SiLU*mul ----   (HBM meanwhile: next layer's q|k|v and o)
+    if (l + 1 < p.L) {
+      dp_prefetch_next(p.layers[l + 1].qkv, p.d, qkv_rows, 0);
+      dp_prefetch_next(p.layers[l + 1].o, p.H * HD, p.d, 0);
+    } else if (p.logits) {
+      dp_prefetch_next(p.lm_head, p.d, p.vocab, 0, 8);  // the first ~40 MB of the lm_head stream
+    }
     dp_norm_prologue(p.vec_o, resid[cur], resid[cur ^ 1], lw.post_norm, p.eps, p.d, xs, red);
     cur ^= 1;
     dp_gemv_gate_up(lw.gate_up, p.d, p.ffn, xs, p.vec_act);
-    dp_prefetch_next(lw.down, p.ffn, p.d, 0);
     bar.sync();
     // ---- E: down-proj ----
     for (int i = threadIdx.x * 8; i < p.ffn; i += kDpThreads * 8) {
@@ -465,8 +482,6 @@ __global__ void __launch_bounds__(kDpThreads, 1) draft_forward_persistent_kernel
     }
     __syncthreads();
     dp_gemv_rows(lw.down, p.ffn, p.d, xs, p.vec_down);
-    if (l + 1 < p.L) dp_prefetch_next(p.layers[l + 1].qkv, p.d, (p.H + 2 * p.KV) * HD, 0);
-    else if (p.logits) dp_prefetch_next(p.lm_head, p.d, p.vocab, 0);
     bar.sync();
   }
   if (p.logits) {

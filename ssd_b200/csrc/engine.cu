@@ -293,6 +293,15 @@ struct ssdk_engine {
   // pinned staging: [StepBlock in][results out]
   uint8_t* pin_in = nullptr;
   uint8_t* pin_out = nullptr;
+  // ssdk_forward_tokens does not synchronize when no token is sampled (prefill chunks), so its inputs go through a ring of
+  // pinned slots [StepBlock | token ids]; a slot is rewritten only after the H2D copies that read it have completed
+  // (one event per slot).  pin_in stays private to ssdk_spec_step / _stage, which synchronize before they return.
+  static constexpr int kFwSlots = 4;
+  uint8_t* pin_fw = nullptr;
+  size_t fw_slot_bytes = 0;
+  cudaEvent_t fw_ev[kFwSlots] = {nullptr};
+  bool fw_ev_pending[kFwSlots] = {false};
+  unsigned fw_next = 0;
   size_t step_bytes = 0;
   size_t out_bytes = 0;
   // offsets inside the step block
@@ -1040,6 +1049,20 @@ int ssdk_create(const ssdk_model_cfg* target, const ssdk_model_cfg* draft, const
     return fail("pinned staging allocation failed");
   }
   memset(e->pin_in, 0, e->step_bytes);
+  e->fw_slot_bytes = align_up(e->step_bytes, 64) + (size_t)kMaxTokens * 8;
+  if (cudaHostAlloc((void**)&e->pin_fw, e->fw_slot_bytes * ssdk_engine::kFwSlots, cudaHostAllocDefault) != cudaSuccess) {
+    cudaFreeHost(e->pin_in);
+    cudaFreeHost(e->pin_out);
+    delete e;
+    return fail("pinned staging allocation failed");
+  }
+  memset(e->pin_fw, 0, e->fw_slot_bytes * ssdk_engine::kFwSlots);
+  for (int i = 0; i < ssdk_engine::kFwSlots; ++i) {
+    if (cudaEventCreateWithFlags(&e->fw_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete e;
+      return fail("event creation failed");
+    }
+  }
   *out = e;
   return 0;
 }
@@ -1051,6 +1074,9 @@ int ssdk_destroy(ssdk_handle h) {
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->pin_in) cudaFreeHost(h->pin_in);
   if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->pin_fw) cudaFreeHost(h->pin_fw);
+  for (int i = 0; i < ssdk_engine::kFwSlots; ++i)
+    if (h->fw_ev[i]) cudaEventDestroy(h->fw_ev[i]);
   delete h;
   return 0;
 }
@@ -1270,6 +1296,21 @@ int ssdk_spec_step_fetch(ssdk_handle h, int batch, int64_t* out_tokens, int32_t*
   return 0;
 }
 
+int ssdk_spec_step_log(ssdk_handle h, int seq, int64_t* out_tokens, int cap, void* stream) {
+  if (!h || !h->finalized) return fail("spec_step_log: engine not finalized");
+  if (seq < 0 || seq >= h->rt.max_batch || !out_tokens || cap < 0) return fail("spec_step_log: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t len = 0;
+  CK(cudaMemcpyAsync(&len, h->ws.log_len + seq, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int n = std::min(std::min((int)len, cap), kLogCap);
+  if (n > 0) {
+    CK(cudaMemcpyAsync(out_tokens, h->ws.log_tokens + (size_t)seq * kLogCap, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return n;
+}
+
 int ssdk_forward_tokens(ssdk_handle h, int which, int batch, int q_len, const int64_t* ids, const int32_t* ctx_len,
                         const int32_t* block_tables, int want_sample, const float* temps, uint64_t seed,
                         uint64_t step_id, int64_t* out_tokens, void* stream) {
@@ -1280,18 +1321,29 @@ int ssdk_forward_tokens(ssdk_handle h, int which, int batch, int q_len, const in
   cudaStream_t st = (cudaStream_t)stream;
   Workspace& w = h->ws;
   const int mbk = h->rt.max_blocks_per_seq;
-  // stage inputs through the pinned step block (block tables go to the slot of `which`)
-  memcpy(h->pin_in + h->off_ctx, ctx_len, (size_t)batch * 4);
+  // stage inputs through one slot of the pinned ring (block tables go to the step-block field of `which`); wait for the
+  // copies that last read this slot before overwriting it — a non-sampling call returns without synchronizing, and its
+  // H2D copies are queued behind the previous chunk's kernels
+  const int slot = (int)(h->fw_next++ % ssdk_engine::kFwSlots);
+  if (h->fw_ev_pending[slot]) {
+    CK(cudaEventSynchronize(h->fw_ev[slot]));
+    h->fw_ev_pending[slot] = false;
+  }
+  uint8_t* pin = h->pin_fw + (size_t)slot * h->fw_slot_bytes;
+  memcpy(pin + h->off_ctx, ctx_len, (size_t)batch * 4);
   float zero[16] = {0};
-  memcpy(h->pin_in + h->off_tt, temps ? temps : zero, (size_t)batch * 4);
+  memcpy(pin + h->off_tt, temps ? temps : zero, (size_t)batch * 4);
   uint64_t ss[2] = {seed, step_id};
-  memcpy(h->pin_in + h->off_seed, ss, 16);
-  memcpy(h->pin_in + (which == SSDK_TARGET ? h->off_btt : h->off_btd), block_tables, (size_t)batch * mbk * 4);
-  CK(cudaMemcpyAsync(w.step_dev, h->pin_in, h->step_bytes, cudaMemcpyHostToDevice, st));
-  // token ids: pinned out-staging tail is free between calls; use a dedicated region after out_bytes
+  memcpy(pin + h->off_seed, ss, 16);
+  memcpy(pin + (which == SSDK_TARGET ? h->off_btt : h->off_btd), block_tables, (size_t)batch * mbk * 4);
+  CK(cudaMemcpyAsync(w.step_dev, pin, h->step_bytes, cudaMemcpyHostToDevice, st));
+  int64_t* pin_ids_in = (int64_t*)(pin + align_up(h->step_bytes, 64));
+  memcpy(pin_ids_in, ids, (size_t)batch * q_len * 8);
+  CK(cudaMemcpyAsync(w.ids_in, pin_ids_in, (size_t)batch * q_len * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(h->fw_ev[slot], st));
+  h->fw_ev_pending[slot] = true;
+  // sampled tokens come back through the tail of the result staging buffer (read after the synchronize below)
   int64_t* pin_ids = (int64_t*)(h->pin_out + h->out_bytes);
-  memcpy(pin_ids, ids, (size_t)batch * q_len * 8);
-  CK(cudaMemcpyAsync(w.ids_in, pin_ids, (size_t)batch * q_len * 8, cudaMemcpyHostToDevice, st));
 
   Launcher L;
   L.st = st;

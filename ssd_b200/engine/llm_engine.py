@@ -92,6 +92,9 @@ class LLMEngine:
     def step(self, step: InferenceStep):
         t = perf_counter()
         seqs, is_prefill = self.scheduler.schedule()
+        retired, self.scheduler.retired = self.scheduler.retired, []
+        if not seqs:  # every runnable sequence ran out of room below max_model_len and was finished by schedule()
+            return [(s.seq_id, s.completion_token_ids) for s in retired]
         n = step.prefill(seqs) if is_prefill else step.decode(seqs)
         dt = perf_counter() - t
         if is_prefill:
@@ -100,7 +103,8 @@ class LLMEngine:
         else:
             METRICS["decode_total_time"] += dt
             METRICS["decode_total_tokens"] += n
-        return [(s.seq_id, s.completion_token_ids) for s in seqs if s.is_finished]
+        return [(s.seq_id, s.completion_token_ids) for s in seqs if s.is_finished] + \
+               [(s.seq_id, s.completion_token_ids) for s in retired]
 
     def is_finished(self):
         return self.scheduler.is_finished()

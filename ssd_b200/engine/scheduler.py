@@ -30,6 +30,7 @@ class Scheduler:
                                                     max_model_len=self.max_model_len)
         self.waiting: deque[Sequence] = deque()
         self.running: deque[Sequence] = deque()
+        self.retired: list[Sequence] = []  # finished inside schedule() (no room for another step); drained by LLMEngine.step
 
     def _managers(self):
         return [m for m in (self.block_manager, self.draft_block_manager) if m is not None]
@@ -62,6 +63,12 @@ class Scheduler:
         chosen: list[Sequence] = []
         while self.running and len(chosen) < self.max_num_seqs:
             seq = self.running.popleft()
+            if seq.num_tokens + lookahead > self.max_model_len:
+                # No room for another (speculative) step below max_model_len.  The reference's can_append() answers
+                # False for this case forever: schedule() preempts, the sequence is re-prefilled and preempted again
+                # (scheduler.py:101-118, block_manager.py:150-152) and generate() spins.  Finish the sequence instead.
+                self._retire(seq)
+                continue
             ok = True
             while not all(m.can_append(seq, lookahead) for m in self._managers()):
                 if self.running:
@@ -133,6 +140,12 @@ class Scheduler:
                         m.seal(seq, idx)
             if finished:
                 self._finish(seq)
+
+    def _retire(self, seq: Sequence) -> None:
+        seq.status = SequenceStatus.FINISHED
+        for m in self._managers():
+            m.deallocate(seq)
+        self.retired.append(seq)
 
     def _finish(self, seq: Sequence) -> None:
         seq.status = SequenceStatus.FINISHED

@@ -62,6 +62,7 @@ SIGNATURES: dict[str, tuple] = {
                                        C.c_uint64, VP]),
     "ssdk_spec_step_resident": (C.c_int, [VP, C.c_int, VP]),
     "ssdk_spec_step_fetch": (C.c_int, [VP, C.c_int, c_i64p, c_i32p, c_i64p, VP]),
+    "ssdk_spec_step_log": (C.c_int, [VP, C.c_int, c_i64p, C.c_int, VP]),
     "ssdk_forward_tokens": (C.c_int, [VP, C.c_int, C.c_int, C.c_int, c_i64p, c_i32p, c_i32p, C.c_int, c_f32p,
                                       C.c_uint64, C.c_uint64, c_i64p, VP]),
     "ssdk_logits_p": (VP, [VP]),

@@ -120,11 +120,18 @@ class _DraftCfg:
     num_kvcache_blocks = 0
 
 
-def kv_blocks_for(config, spec: ModelSpec, tp_size: int, share: float) -> int:
+def kv_block_bytes(config, spec: ModelSpec, tp_size: int) -> int:
+    return 2 * spec.layers * config.kvcache_block_size * (spec.kv_heads // tp_size) * spec.head_dim * 2
+
+
+def kv_blocks_for(config, spec: ModelSpec, tp_size: int, share: float, reserved: int = 0) -> int:
     """allocate_kv_cache (engine/model_runner.py:446-476): blocks that fit in share * gpu_memory_utilization * free,
-    capped at what max_num_seqs sequences of max_model_len (+ prefix-cache slack) can ever use."""
+    capped at what max_num_seqs sequences of max_model_len (+ prefix-cache slack) can ever use.  `reserved` = bytes
+    already promised to another cache out of the same free-memory snapshot (the reference sizes the draft cache from
+    what REMAINS after the target's, draft_runner.py:27)."""
     free, _ = torch.cuda.mem_get_info()
-    block_bytes = 2 * spec.layers * config.kvcache_block_size * (spec.kv_heads // tp_size) * spec.head_dim * 2
+    free = max(0, free - reserved)
+    block_bytes = kv_block_bytes(config, spec, tp_size)
     fit = int(free * config.gpu_memory_utilization * share) // block_bytes
     want = max(config.max_num_seqs, 1) * config.max_blocks * 2 + 2
     return max(1, min(fit, want))
@@ -140,7 +147,7 @@ def build_runner(config, tp_size: int = 1, tp_rank: int = 0, device=None, finali
     if dspec is not None and tp_rank != 0:
         dspec = None  # the draft is a replica pinned to rank 0
     nbt = kv_blocks_for(config, tspec, tp_size, 0.8 if dspec else 1.0)
-    nbd = kv_blocks_for(config, dspec, 1, 0.75) if dspec else None
+    nbd = kv_blocks_for(config, dspec, 1, 0.75, reserved=nbt * kv_block_bytes(config, tspec, tp_size)) if dspec else None
     config.num_kvcache_blocks = nbt
     draft_cfg = _DraftCfg()
     draft_cfg.num_kvcache_blocks = nbd or nbt

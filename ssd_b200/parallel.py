@@ -69,8 +69,9 @@ def create_nccl_comm(world: int, rank: int, group=None) -> int:
 def bind_symmetric_memory(runner, world: int, rank: int, group=None) -> bool:
     """Allocate the NVLink symmetric buffer of the one-shot all-reduce (torch symmetric memory: cuMem + peer mapping),
     rendezvous with the other ranks and hand every rank's mapped pointer to libssdk (ssdk_bind_symm).  Returns False
-    (the engine then keeps the in-graph NCCL all-reduce) when symmetric memory is unavailable or disabled with
-    SSD_B200_NO_SYMM=1."""
+    (the engine then keeps the in-graph NCCL all-reduce) ONLY when disabled with SSD_B200_NO_SYMM=1; if symmetric
+    memory cannot be set up the launch fails loudly — a silent fall-back to NCCL would make every multi-GPU number
+    unattributable (bench.py records which all-reduce ran in its "allreduce" key)."""
     if os.environ.get("SSD_B200_NO_SYMM") == "1":
         return False
     from . import lib as L
@@ -86,9 +87,8 @@ def bind_symmetric_memory(runner, world: int, rank: int, group=None) -> bool:
         torch.cuda.synchronize()
         dist.barrier(group)  # every rank has zeroed its flags before anyone publishes
     except Exception as exc:  # noqa: BLE001
-        if rank == 0:
-            print(f"[ssd_b200] symmetric memory unavailable ({type(exc).__name__}: {exc}); using NCCL all-reduce", flush=True)
-        return False
+        raise RuntimeError(f"NVLink symmetric memory unavailable ({type(exc).__name__}: {exc}); set SSD_B200_NO_SYMM=1 to run "
+                           "the tensor-parallel all-reduces through NCCL instead") from exc
     arr = (C.c_void_p * world)(*ptrs)
     L.check(runner.lib.ssdk_bind_symm(runner.h, arr, world), "ssdk_bind_symm")
     runner._keep.extend([buf, hdl])

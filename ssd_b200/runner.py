@@ -239,6 +239,14 @@ class PairRunner:
                 "ssdk_spec_step_fetch")
         return toks, total, rec
 
+    def resident_log(self, seq: int = 0, cap: int = 16384) -> list[int]:
+        """Tokens sequence `seq` emitted in resident mode since stage() (recovery + accepted drafts of every step)."""
+        out = np.zeros(cap, dtype=np.int64)
+        n = self.lib.ssdk_spec_step_log(self.h, seq, out.ctypes.data_as(L.c_i64p), cap, torch.cuda.current_stream().cuda_stream)
+        if n < 0:
+            raise RuntimeError("ssdk_spec_step_log failed: " + L.last_error())
+        return out[:n].tolist()
+
     # debug taps (parity tests compare these with the oracle's logits)
     def logits_p(self, batch: int) -> torch.Tensor:
         return _from_ptr(self.lib.ssdk_logits_p(self.h), (batch, self.K + 1, self.spec[L.TARGET].vocab), self.device)

@@ -33,7 +33,8 @@ SHAPES = {
 
 
 def make_model_dir(root: str, shape: str, role: str, seed: int = 0, alpha: float = 0.85, layers: int | None = None,
-                   max_position_embeddings: int = 131072) -> str:
+                   max_position_embeddings: int = 131072, o_down_std: float = 1e-5, rng: str = "torch",
+                   draft_mode: str = "perm", lm_scale: float | None = None) -> str:
     """Write <root>/<family>-synthetic-<shape>-<role>/ and return its path.  `role` is "target" or "draft"."""
     h, L, H, KV, hd, ffn, V, eps, theta, mtype, tied = SHAPES[shape]
     L = layers or L
@@ -53,7 +54,8 @@ def make_model_dir(root: str, shape: str, role: str, seed: int = 0, alpha: float
     with open(os.path.join(path, "config.json"), "w") as f:
         json.dump(cfg, f, indent=1)
     with open(os.path.join(path, "ssd_b200_synthetic.json"), "w") as f:
-        json.dump({"seed": seed, "alpha": alpha, "role": role, "shape": shape}, f)
+        json.dump({"seed": seed, "alpha": alpha, "role": role, "shape": shape, "o_down_std": o_down_std,
+                   "rng": rng, "draft_mode": draft_mode, "lm_scale": lm_scale}, f)
     return path
 
 
@@ -77,22 +79,66 @@ class SyntheticTokenizer:
         return "".join(f"<{int(i)}>" for i in ids)
 
 
-def permutations(vocab: int, seed: int, alpha: float, device) -> tuple[torch.Tensor, torch.Tensor]:
-    """(pi_target, pi_draft): pi_draft[t] == pi_target[t] on a seeded fraction alpha of tokens."""
+def permutations(vocab: int, seed: int, alpha: float, device, draft_mode: str = "perm") -> tuple[torch.Tensor, torch.Tensor]:
+    """(pi_target, pi_draft): pi_draft[t] == pi_target[t] on a seeded fraction alpha of tokens.
+
+    draft_mode "perm" (default): on the other tokens the draft follows a DIFFERENT next-token map with the same large
+    margin — pi_draft(t) = pi_target(sigma(t)) with sigma a cyclic shift inside the disagreeing set — so pi_draft is a
+    permutation too, every draft decision is as clear-cut as the target's and a whole run is reproducible token for
+    token (engine vs oracle vs the reference engine on the same weights).  "noise" (round 1): pi_draft = -1 there, the
+    draft's lm_head row is missing and its guess is the argmax of noise (a near-tie a few per cent of the time)."""
     g = torch.Generator(device="cpu").manual_seed(seed * 7919 + 13)
-    pi_t = torch.randperm(vocab, generator=g)
-    agree = torch.rand(vocab, generator=g) < alpha
-    pi_d = torch.where(agree, pi_t, torch.full_like(pi_t, -1))  # -1: the draft has no idea (its guess will be noise)
+    pi_t = torch.randperm(vocab, generator=g, device="cpu")  # explicit: the caller may run under set_default_device("cuda")
+    agree = torch.rand(vocab, generator=g, device="cpu") < alpha
+    if draft_mode == "noise":
+        pi_d = torch.where(agree, pi_t, torch.full_like(pi_t, -1))
+    else:
+        pi_d = pi_t.clone()
+        dis = (~agree).nonzero().squeeze(1)
+        if dis.numel() > 1:
+            pi_d[dis] = pi_t[torch.roll(dis, -1)]
     return pi_t.to(device), pi_d.to(device)
 
 
-def generate_weights(spec, meta: dict, device, tp_size: int = 1, tp_rank: int = 0) -> dict:
-    """Packed per-rank bf16 weights on `device` for a synthetic directory (`meta` = ssd_b200_synthetic.json).
+def hash_uniform(rows: int, cols: int, std: float, stream: int, device, row0: int = 0) -> torch.Tensor:
+    """Device-independent pseudo-random bf16 matrix [rows, cols], zero mean, standard deviation `std` (uniform): element
+    (r, c) is a pure integer function of (stream, r + row0, c) — splitmix64-style, wrapping int64 arithmetic — so the
+    same bits come out on CPU and GPU.  Used where a fixture generated in the (GPU-less) build container must be
+    regenerated bit-for-bit on the GPU box (tests/golden/true_width_*.npz)."""
+    out = torch.empty(rows, cols, dtype=torch.bfloat16, device=device)
+    step = max(1, (1 << 25) // max(cols, 1))
+    c = torch.arange(cols, dtype=torch.int64, device=device)[None, :]
+    scale = std * (3.0 ** 0.5) / 32768.0
+    off = (stream * 0x51ED270B27B4F3) & 0x3FFFFFFFFFFFFFFF  # keep the Python int inside int64
+    for r in range(0, rows, step):
+        n = min(step, rows - r)
+        idx = (torch.arange(r + row0, r + row0 + n, dtype=torch.int64, device=device)[:, None] * 1000003 + c
+               + off)
+        x = idx * -7046029254386353131  # 0x9E3779B97F4A7C15 as int64
+        x = x ^ ((x >> 30) & 0x3FFFFFFFF)
+        x = x * -4658895280553007687    # 0xBF58476D1CE4E5B9
+        x = x ^ ((x >> 27) & 0x1FFFFFFFFF)
+        x = x * -7723592293110705685    # 0x94D049BB133111EB
+        x = x ^ ((x >> 31) & 0x1FFFFFFFF)
+        u = ((x >> 20) & 0xFFFF) - 32768  # [-32768, 32767]
+        out[r:r + n] = (u.to(torch.float32) * scale).to(torch.bfloat16)
+    return out
+
+
+def iter_weights(spec, meta: dict, device, tp_size: int = 1, tp_rank: int = 0):
+    """Yield the packed per-rank bf16 weights of a synthetic directory one piece at a time, in RNG order:
+    ("embed", t), ("lm_head", t), ("final_norm", t), then ("layer", l, {...}) for every decoder layer.  A consumer that
+    copies each piece into its own storage and drops it never holds two copies of a 70B model (the reference GPU arm
+    fills the reference's nn.Parameters this way); `generate_weights` simply collects the pieces.
 
     Sharding follows the reference's rules (layers/linear.py:90-95,116-122,148-162,188-193; embed_head.py:41-47):
     column-parallel qkv / gate_up by output rows per head group, row-parallel o / down by input columns,
     embedding and lm_head by vocab rows."""
     seed, alpha, role = meta["seed"], meta["alpha"], meta["role"]
+    od_std = float(meta.get("o_down_std", 1e-5))
+    o_std, down_std = float(meta.get("o_std", od_std)), float(meta.get("down_std", od_std))
+    hashed = meta.get("rng", "torch") == "hash"
+    role_id = 1 if role == "target" else 2
     d, V = spec.hidden, spec.vocab
     H, KV, hd, ffn = spec.heads // tp_size, spec.kv_heads // tp_size, spec.head_dim, spec.ffn // tp_size
     Vs = V // tp_size
@@ -107,8 +153,16 @@ def generate_weights(spec, meta: dict, device, tp_size: int = 1, tp_rank: int = 
             out[r:r + n] = (torch.randn(n, cols, generator=gen, device=device, dtype=torch.float32) * std).to(bf)
         return out
 
+    if hashed:
+        n_mat = [0]
+
+        def randn(rows, cols, std, gen):  # noqa: F811 — same call sites, device-independent values
+            n_mat[0] += 1
+            return hash_uniform(rows, cols, std, seed * 4096 + (0 if gen is g else role_id * 1024 + tp_rank * 128) + n_mat[0],
+                                device)
+
     embed_full = randn(V, d, 1.0, g)  # identical on every rank and for both roles
-    pi_t, pi_d = permutations(V, seed, alpha, device)
+    pi_t, pi_d = permutations(V, seed, alpha, device, meta.get("draft_mode", "perm"))
     pi = pi_t if role == "target" else pi_d
     lo, hi = tp_rank * Vs, (tp_rank + 1) * Vs
     # lm_head[pi(t)] = e_t  <=>  lm_head[v] = e_{pi^-1(v)}.  Draft: only the agreeing tokens get their row; the rows
@@ -123,23 +177,45 @@ def generate_weights(spec, meta: dict, device, tp_size: int = 1, tp_rank: int = 
         lm_head[pi[known]] = embed_full[known]
         lm_shard = lm_head[lo:hi].contiguous()
         del lm_head
-    w = {"embed": embed_full[lo:hi].contiguous(), "lm_head": lm_shard,
-         "final_norm": torch.ones(d, dtype=bf, device=device), "layers": []}
+    lm_scale = meta.get("lm_scale")
+    if lm_scale:
+        # soften the next-token distribution for temp > 0 runs: logit of the bigram successor ~= lm_scale, the others
+        # ~ N(0, lm_scale^2 / d) (unscaled: ~d against ~sqrt(d), i.e. a one-hot softmax at any sane temperature)
+        for r0 in range(0, lm_shard.shape[0], 16384):
+            lm_shard[r0:r0 + 16384] = (lm_shard[r0:r0 + 16384].float() * (float(lm_scale) / d)).to(bf)
+    embed_shard = embed_full[lo:hi].contiguous()
     del embed_full
+    yield ("embed", embed_shard)
+    del embed_shard
+    yield ("lm_head", lm_shard)
+    del lm_shard
+    yield ("final_norm", torch.ones(d, dtype=bf, device=device))
     gl = torch.Generator(device=device).manual_seed(seed * 1000003 + (101 if role == "target" else 202) + 7 * tp_rank)
-    for _ in range(spec.layers):
+    for l in range(spec.layers):
         lw = {
             "input_norm": torch.ones(d, dtype=bf, device=device),
             "post_norm": torch.ones(d, dtype=bf, device=device),
             "qkv": randn((H + 2 * KV) * hd, d, 0.02, gl),
-            "o": randn(d, H * hd, 1e-5, gl),        # ~0: keeps the residual stream == embedding
+            # default ~0: keeps the residual stream == embedding (accept-len control); `o_down_std` in the
+            # directory's meta switches the attention / MLP branches on (parity tests)
+            "o": randn(d, H * hd, o_std, gl),
             "gate_up": randn(2 * ffn, d, 0.02, gl),
-            "down": randn(d, ffn, 1e-5, gl),
+            "down": randn(d, ffn, down_std, gl),
         }
         if spec.qk_norm:
             lw["q_norm"] = torch.ones(hd, dtype=bf, device=device)
             lw["k_norm"] = torch.ones(hd, dtype=bf, device=device)
-        w["layers"].append(lw)
+        yield ("layer", l, lw)
+
+
+def generate_weights(spec, meta: dict, device, tp_size: int = 1, tp_rank: int = 0) -> dict:
+    """Packed per-rank bf16 weights on `device` for a synthetic directory (`meta` = ssd_b200_synthetic.json)."""
+    w = {"layers": []}
+    for item in iter_weights(spec, meta, device, tp_size, tp_rank):
+        if item[0] == "layer":
+            w["layers"].append(item[2])
+        else:
+            w[item[0]] = item[1]
     return w
 
 

@@ -62,8 +62,8 @@ def test_spec_steps_match_oracle(family, use_graph):
     for b in range(B):
         rec.append(r.prefill(L.TARGET, prompts[b], bt[b].tolist()))
         r.prefill(L.DRAFT, prompts[b], bt[b].tolist(), want_sample=False)
-    # prefill logits of the last sequence vs oracle, then the sampled first tokens
-    assert rec == rec_o or True
+    # the first sampled tokens: engine == oracle == the reference's golden trace
+    assert rec == rec_o, f"first tokens {rec} vs oracle {rec_o}"
     ctx = [len(p) for p in prompts]
     assert rec == z["rec0"].tolist(), f"first tokens {rec} vs reference {z['rec0'].tolist()}"
     soft_total = 0
@@ -91,14 +91,21 @@ def test_spec_steps_match_oracle(family, use_graph):
     r.close()
 
 
-def test_trace_matches_reference_tokens():
-    """Follow the REFERENCE's golden trace (tests/golden/trace_llama.npz): same prompts, the reference's recovery tokens
-    and context lengths.  The engine must reproduce the reference's speculations / accept counts step by step; the first
-    step where it does not must be a near-tie (top-2 logit margin < EPS under the oracle), after which the KV state no
-    longer follows the golden path and the comparison stops."""
+# golden steps (of 10, two sequences each) that must be reproduced EXACTLY — speculations, accept counts and recovery
+# tokens of both sequences — before any near-tie may end the comparison; measured on B200 (profiles/r02_pytest_gpu.txt)
+MIN_EXACT_GOLDEN_STEPS = {"llama": 1, "qwen": 1}
+
+
+@pytest.mark.parametrize("family", ["llama", "qwen"])
+def test_trace_matches_reference_tokens(family):
+    """Follow the REFERENCE's golden trace (tests/golden/trace_<family>.npz, produced by running the reference's own
+    model classes, Sampler and verify()): same prompts, the reference's recovery tokens and context lengths.  The engine
+    must reproduce the reference's speculations / accept counts / recovery tokens step by step; the first step where it
+    does not must be a near-tie (top-2 logit margin < EPS under the oracle), after which the KV state no longer follows
+    the golden path and the comparison stops.  The number of exactly reproduced steps is reported and has a floor."""
     from oracle.spec import check_greedy_step
     from ssd_b200 import lib as L
-    z, r, s, bt, K = _build("llama", True)
+    z, r, s, bt, K = _build(family, True)
     prompts = [z["prompt0"].tolist(), z["prompt1"].tolist()]
     B = 2
     s.prefill(prompts, [0.0, 0.0], bt, bt.clone())
@@ -128,7 +135,8 @@ def test_trace_matches_reference_tokens():
         s.spec_step_forced(torch.from_numpy(z["spec"][step]))  # keep the oracle's KV on the golden path
         s.advance(z["nacc"][step].tolist(), nxt)
         ctx = [c + int(n) + 1 for c, n in zip(ctx, z["nacc"][step])]
-    assert same >= 1, "not even the first step reproduces the reference trace"
+    print(f"[golden trace {family}] {same}/{n_steps} steps reproduced exactly (tokens, accept counts, recovery; 2 sequences)")
+    assert same >= MIN_EXACT_GOLDEN_STEPS[family], f"only {same} golden steps reproduced exactly"
     r.close()
 
 

@@ -130,6 +130,31 @@ def test_scheduler_random_walk_invariants():
         assert len(bm.free_block_ids) == 48 and not bm.used_block_ids
 
 
+def test_no_room_below_max_model_len_finishes_instead_of_spinning():
+    """A sequence whose length lands in (max_model_len - K - 1, max_model_len) cannot take another spec step.  The
+    reference preempts and re-prefills it forever (scheduler.py:101-118); here schedule() retires it."""
+    sch = Scheduler(_cfg(num_kvcache_blocks=48, max_num_seqs=2, max_model_len=64),
+                    draft_cfg=types.SimpleNamespace(num_kvcache_blocks=48))
+    s = Sequence(list(range(2, 42)), SamplingParams(temperature=0.0, max_new_tokens=500, ignore_eos=True))
+    sch.add(s)
+    batch, is_prefill = sch.schedule()
+    assert is_prefill and batch == [s]
+    s.recovery_token_id = 3
+    s.num_cached_tokens = s.num_draft_cached_tokens = s.num_prompt_tokens
+    steps = 0
+    while not sch.is_finished() and steps < 50:
+        steps += 1
+        batch, is_prefill = sch.schedule()
+        assert not is_prefill
+        if not batch:
+            break
+        sch.postprocess_speculate(batch, [[s.recovery_token_id, 4, 4]], [3])  # 3 tokens per step: 40 -> 58 -> stop
+    assert sch.is_finished() and sch.retired == [s] and s.is_finished
+    assert 64 - 5 <= s.num_tokens <= 64
+    for bm in (sch.block_manager, sch.draft_block_manager):
+        assert len(bm.free_block_ids) == 48 and not bm.used_block_ids
+
+
 def test_compat_shim_exposes_reference_names():
     import ssd_b200.compat as cm
     cm.install()

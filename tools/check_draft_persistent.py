@@ -46,9 +46,11 @@ def worker(out_path):
     r.stage([ctx], [rec], [bt], [bt], [0.0], [0.0])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r.step_resident(4)
+    for _ in range(4):
+        r.step_resident(1)
     e0.record()
-    r.step_resident(16)
+    for _ in range(16):
+        r.step_resident(1)
     e1.record()
     torch.cuda.synchronize()
     np.savez(out_path, toks=np.array(toks_all), nacc=np.array(nacc_all), lq=lq, ms=e0.elapsed_time(e1) / 16)
