@@ -123,7 +123,22 @@ SSDK_DEVINL float u32_to_unit_open0(uint32_t x) {
 // Exp(1) sample from one 32-bit word
 SSDK_DEVINL float u32_to_exp1(uint32_t x) { return -__logf(u32_to_unit_open0(x)); }
 
+// epoch / slot parity of the one-shot all-reduce number call_idx of target forward number seq (n_calls all-reduces per
+// forward).  The slot parity runs on ACROSS forwards: a forward has 2L+1 all-reduces — an odd number — so a per-forward
+// parity would put the last all-reduce of forward n and the first one of forward n+1 into the same slot back to back, and
+// a fast rank could overwrite words a slow peer is still polling.  With a continuous parity a slot is reused at
+// distance 2 only, which the data dependence already protects (a rank needs every peer's words of all-reduce i+1 before
+// it can publish i+2).
+SSDK_DEVINL unsigned symm_epoch_of(unsigned seq, int call_idx) { return seq * 512u + (unsigned)call_idx + 1u; }
+SSDK_DEVINL unsigned symm_parity_of(unsigned seq, int call_idx, int n_calls) {
+  return (seq * (unsigned)n_calls + (unsigned)call_idx) & 1u;
+}
+
 #ifndef SSDK_HOST_EMU
+// one 8-byte store (flag-in-word protocol: payload and flag must become visible together)
+SSDK_DEVINL void st_global_v2_u32(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
 // ----------------------------------------------------------------------------------
 // PTX: shared-address conversion, mbarrier, fences
 // ----------------------------------------------------------------------------------
@@ -178,6 +193,18 @@ SSDK_DEVINL void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, in
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
       "l"(policy)
       : "memory");
+}
+
+// non-tensor bulk copy global -> shared (contiguous bytes; 16-byte aligned addresses and size), mbarrier completion, weights
+// tagged evict-first in L2; and its fire-and-forget sibling that only pulls the bytes into L2
+SSDK_DEVINL void bulk_load_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictFirst)
+      : "memory");
+}
+SSDK_DEVINL void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
 // ----------------------------------------------------------------------------------
@@ -342,6 +369,47 @@ SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 }
 SSDK_DEVINL void prefetch_l2(const void*) {}
+// mbarrier + bulk copy stand-ins: one 64-bit word = {phase bit 63 | pending arrivals 32..47 | init count 48..62 | tx bytes 0..31},
+// updated under one global lock (test infrastructure; the bulk copy is a synchronous memcpy by the issuing thread)
+inline std::mutex& emu_mbar_mu() {
+  static std::mutex m;
+  return m;
+}
+inline void emu_mbar_settle(uint64_t& w) {
+  const uint64_t pending = (w >> 32) & 0xFFFFu, init = (w >> 48) & 0x7FFFu;
+  if (pending == 0 && (uint32_t)w == 0u) w = ((w ^ (1ull << 63)) & ~(0xFFFFull << 32)) | (init << 32);
+}
+SSDK_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+  std::lock_guard<std::mutex> g(emu_mbar_mu());
+  *bar = ((uint64_t)count << 48) | ((uint64_t)count << 32);
+}
+SSDK_DEVINL void fence_mbar_init() {}
+SSDK_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  std::lock_guard<std::mutex> g(emu_mbar_mu());
+  uint64_t w = *bar;
+  w = (w & ~0xFFFFFFFFull) | (uint32_t)((uint32_t)w + bytes);
+  w -= (1ull << 32);
+  emu_mbar_settle(w);
+  *bar = w;
+}
+SSDK_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> g(emu_mbar_mu());
+      if ((uint32_t)(*bar >> 63) != parity) return;
+    }
+    std::this_thread::yield();
+  }
+}
+SSDK_DEVINL void bulk_load_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  std::memcpy(smem_dst, gsrc, bytes);
+  std::lock_guard<std::mutex> g(emu_mbar_mu());
+  uint64_t w = *bar;
+  w = (w & ~0xFFFFFFFFull) | (uint32_t)((uint32_t)w - bytes);
+  emu_mbar_settle(w);
+  *bar = w;
+}
+SSDK_DEVINL void bulk_prefetch_l2(const void*, uint32_t) {}
 SSDK_DEVINL uint4 ld_volatile_v4(const void* p) {
   // two aligned 8-byte words {2 x bf16, epoch}: each is read atomically, like the device's 8-byte store granularity
   const uint64_t* q = reinterpret_cast<const uint64_t*>(p);

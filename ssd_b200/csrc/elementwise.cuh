@@ -139,13 +139,15 @@ __global__ void prep_kernel(const int32_t* __restrict__ ctx0, const int32_t* __r
 // vector stores (an aligned 8-byte store is atomic, so data and flag become visible together — no fence, no separate
 // signal), and the consumer simply re-reads a word until its flag equals the expected epoch.  The epoch is
 // (target-forward sequence number) * 512 + (static index of the all-reduce inside the forward) + 1, so it needs no
-// cross-kernel bookkeeping and a static CUDA graph can replay it.  Slots are double-buffered by call parity; a rank
-// cannot run two all-reduces ahead of a peer because it needs that peer's words of the previous one first.
+// cross-kernel bookkeeping and a static CUDA graph can replay it.  Slots are double-buffered by a parity that runs on
+// across forwards (symm_parity_of, common.cuh); a rank cannot run two all-reduces ahead of a peer because it needs that
+// peer's words of the previous one first.
 struct SymmIn {
   const uint8_t* base;      // this rank's symmetric buffer; nullptr = not used
   const unsigned* fwd_seq;  // local: sequence number of the current target forward
   int no_dep_wait;          // 1: the consumer may skip griddepcontrol.wait (see add_rmsnorm_kernel)
   int call_idx;             // static index of this all-reduce inside the forward
+  int n_calls;              // all-reduces per forward (slot parity runs on across forwards, see symm_parity_of)
   int n_ranks;
   unsigned slot_bytes;
 };
@@ -155,9 +157,8 @@ constexpr int kSymmMaxRanks = 8;
 // whole PDL chain (>= 9 launches) were co-resident and launched within prep's ~2 us — impossible at model shapes
 // (the GEMM grids serialise the chain) and never observed, but not excluded by construction.  Moving the bump into a
 // one-thread kernel after the forward's last consumer makes it stable long before the next forward starts.
-SSDK_DEVINL unsigned symm_epoch(const unsigned* fwd_seq, int call_idx) { return __ldcg(fwd_seq) * 512u + (unsigned)call_idx + 1u; }
-SSDK_DEVINL size_t symm_slot_off(int call_idx, int rank, unsigned slot_bytes) {
-  return ((size_t)(call_idx & 1) * kSymmMaxRanks + rank) * slot_bytes;
+SSDK_DEVINL size_t symm_slot_off(unsigned parity, int rank, unsigned slot_bytes) {
+  return ((size_t)parity * kSymmMaxRanks + rank) * slot_bytes;
 }
 
 struct NormParams {
@@ -269,8 +270,9 @@ __global__ void __launch_bounds__(512) add_rmsnorm_kernel(NormParams p) {
   const uint8_t* symm_slots = nullptr;
   unsigned symm_e = 0;
   if (p.symm.base) {
-    symm_e = symm_epoch(p.symm.fwd_seq, p.symm.call_idx);
-    symm_slots = p.symm.base + symm_slot_off(p.symm.call_idx, 0, p.symm.slot_bytes);
+    const unsigned seq = __ldcg(p.symm.fwd_seq);
+    symm_e = symm_epoch_of(seq, p.symm.call_idx);
+    symm_slots = p.symm.base + symm_slot_off(symm_parity_of(seq, p.symm.call_idx, p.symm.n_calls), 0, p.symm.slot_bytes);
   }
   const __nv_bfloat16* erow = nullptr;
   bool zero_row = false;
@@ -358,15 +360,16 @@ struct ArPublishParams {
   uint8_t* peer[kSymmMaxRanks];
   unsigned slot_bytes;
   const unsigned* fwd_seq;
-  int call_idx;
+  int call_idx, n_calls;
 };
 
 __global__ void __launch_bounds__(256) ar_publish_kernel(ArPublishParams p) {
   pdl_launch_dependents();
   pdl_wait();
   if (threadIdx.x == 0) trace_mark(TR_MISC);
-  const unsigned e = symm_epoch(p.fwd_seq, p.call_idx);
-  const size_t slot_off = symm_slot_off(p.call_idx, p.rank, p.slot_bytes);
+  const unsigned seq = __ldcg(p.fwd_seq);
+  const unsigned e = symm_epoch_of(seq, p.call_idx);
+  const size_t slot_off = symm_slot_off(symm_parity_of(seq, p.call_idx, p.n_calls), p.rank, p.slot_bytes);
   const int total = p.M * p.d;
   for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) * 8; idx < total; idx += gridDim.x * blockDim.x * 8) {
     const int m = idx / p.d, i = idx - m * p.d;

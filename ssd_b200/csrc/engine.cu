@@ -18,10 +18,10 @@
 #include "../../include/ssdk.h"
 #include "attention.cuh"
 #include "common.cuh"
-#include "draft_persistent.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "sampling.cuh"
+#include "draft_stream.cuh"
 
 using namespace ssdk;
 typedef __nv_bfloat16 bf16;
@@ -176,9 +176,9 @@ static int launch_gemm(Launcher& L, int umma_n, int epi, const CUtensorMap& tmW,
                        const GemmParams& p, int tiles, int splits) {
 #define SSDK_GEMM_CASE(UN, EP) \
   if (umma_n == UN && epi == EP) return launch_gemm_inst<UN, EP>(L, tmW, tmX, p, tiles, splits);
-  SSDK_GEMM_CASE(16, EPI_BF16) SSDK_GEMM_CASE(16, EPI_PARTIAL) SSDK_GEMM_CASE(16, EPI_SILU)
-  SSDK_GEMM_CASE(32, EPI_BF16) SSDK_GEMM_CASE(32, EPI_PARTIAL) SSDK_GEMM_CASE(32, EPI_SILU)
-  SSDK_GEMM_CASE(64, EPI_BF16) SSDK_GEMM_CASE(64, EPI_PARTIAL) SSDK_GEMM_CASE(64, EPI_SILU)
+  SSDK_GEMM_CASE(16, EPI_BF16) SSDK_GEMM_CASE(16, EPI_PARTIAL) SSDK_GEMM_CASE(16, EPI_SILU) SSDK_GEMM_CASE(16, EPI_PUBLISH)
+  SSDK_GEMM_CASE(32, EPI_BF16) SSDK_GEMM_CASE(32, EPI_PARTIAL) SSDK_GEMM_CASE(32, EPI_SILU) SSDK_GEMM_CASE(32, EPI_PUBLISH)
+  SSDK_GEMM_CASE(64, EPI_BF16) SSDK_GEMM_CASE(64, EPI_PARTIAL) SSDK_GEMM_CASE(64, EPI_SILU) SSDK_GEMM_CASE(64, EPI_PUBLISH)
 #undef SSDK_GEMM_CASE
   return fail("no GEMM instance for umma_n=%d epi=%d", umma_n, epi);
 }
@@ -245,7 +245,8 @@ struct Workspace {
   float* partials;
   float *att_o, *att_lse;
   unsigned* att_counters;
-  unsigned* ar_state;  // [0] epoch of the last published all-reduce, [1] publish ticket
+  unsigned* ar_state;  // [0] sequence number of the running target forward (epoch base of its one-shot all-reduces)
+  unsigned* pub_counters;  // [512] split-K arrival tickets of the in-kernel reductions (EPI_PUBLISH / split EPI_SILU), zero between launches
   int64_t* positions;
   int32_t *slot_mapping, *context_lens;
   // step state
@@ -269,10 +270,10 @@ struct Workspace {
   RecPart* ver_rec;
   unsigned* ver_counters;
   size_t partial_floats = 0;
-  // persistent draft forward (experimental): inter-phase vectors, split-KV partials, barrier state
-  bf16* dp_vec;
-  float* dp_attn;
-  unsigned* dp_sync;
+  // streaming draft kernel (draft_stream.cuh): inter-phase vectors, split-KV partials, device-wide barrier state
+  bf16* ds_vec;
+  float* ds_attn;
+  unsigned* ds_sync;
 };
 
 constexpr int kSampleChunks = 64;
@@ -379,6 +380,7 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.att_lse = (float*)take((size_t)kMaxTokens * Hmax * kAttnMaxSplit * 4);
   w.att_counters = (unsigned*)take((size_t)kMaxTokens * 64 * 4);
   w.ar_state = (unsigned*)take(64);
+  w.pub_counters = (unsigned*)take(512 * 4);
   w.positions = (int64_t*)take(kMaxTokens * 8);
   w.slot_mapping = (int32_t*)take(kMaxTokens * 4);
   w.context_lens = (int32_t*)take(kMaxTokens * 4);
@@ -401,9 +403,9 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.ver_rows = (RowPart*)take((size_t)kVerifyMaxRows * kVerifyCtas * sizeof(RowPart));
   w.ver_rec = (RecPart*)take((size_t)16 * kVerifyCtas * sizeof(RecPart));
   w.ver_counters = (unsigned*)take(64);
-  w.dp_vec = (bf16*)take((size_t)(qmax + 4 * dmax + fmax + 64) * 2);
-  w.dp_attn = (float*)take((size_t)Hmax * kDpSplits * (hdmax + 2) * 4);
-  w.dp_sync = (unsigned*)take(64);
+  w.ds_vec = (bf16*)take((size_t)(qmax + 4 * dmax + fmax + 64) * 2);
+  w.ds_attn = (float*)take((size_t)Hmax * kDsSplits * (hdmax + 2) * 4);
+  w.ds_sync = (unsigned*)take(64);
   return (int64_t)align_up(off, 1024);
 }
 
@@ -485,7 +487,7 @@ static int enqueue_attention(Launcher& L, const bf16* q, const bf16* kc, const b
 }
 
 static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w, int M, int epi, void* out, int ldo,
-                        int N_out, int* splits_out) {
+                        int N_out, int* splits_out, const PublishParams* pub = nullptr) {
   CKI(weight_tmap(w));
   const int K = (int)w.cols;
   if (K % kBlockK) return fail("GEMM K=%d not a multiple of 64", K);
@@ -495,16 +497,29 @@ static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w
   GemmParams p;
   p.out = out; p.M = M; p.N = N_out; p.ldo = ldo; p.num_kb = K / kBlockK;
   int tiles, splits;
+  p.sk_partials = nullptr; p.sk_counters = nullptr; p.sk_width = 0;
   if (epi == EPI_SILU) {
     tiles = (N_out + 63) / 64;
-    splits = 1;
+    // narrow (tensor-parallel) shards: too few 64-column tiles to fill the machine -> split K, reduced inside the kernel
+    splits = (tiles < num_sms() && out != nullptr && e->ws.partials) ? auto_splits(tiles, p.num_kb) : 1;
+    if (splits > 1 && (tiles > 512 || (size_t)splits * M * 2 * N_out > e->ws.partial_floats)) splits = 1;
     p.tile_rows = 64;
     p.hi_row_offset = N_out;
+    if (splits > 1) {
+      p.sk_partials = e->ws.partials; p.sk_counters = e->ws.pub_counters; p.sk_width = 2 * N_out;
+    }
   } else {
     tiles = (N_out + kTileRows - 1) / kTileRows;
-    splits = (epi == EPI_PARTIAL) ? auto_splits(tiles, p.num_kb) : 1;
+    splits = (epi == EPI_PARTIAL || epi == EPI_PUBLISH) ? auto_splits(tiles, p.num_kb) : 1;
     p.tile_rows = kTileRows;
     p.hi_row_offset = 64;
+  }
+  if (epi == EPI_PUBLISH) {
+    if (!pub) return fail("EPI_PUBLISH without publish parameters");
+    if (tiles > 512) return fail("EPI_PUBLISH: %d tiles > 512 ticket counters", tiles);
+    if ((size_t)splits * M * N_out > e->ws.partial_floats) return fail("split-K partial buffer too small");
+    p.pub = *pub;
+    p.sk_partials = e->ws.partials; p.sk_counters = e->ws.pub_counters; p.sk_width = N_out;
   }
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   if (epi == EPI_PARTIAL && (size_t)splits * M * N_out > e->ws.partial_floats && out == e->ws.partials)
@@ -521,6 +536,7 @@ static SymmIn symm_in(ssdk_engine* e, int call_idx, bool no_dep_wait = false) {
   s.base = e->symm_peer[e->model[SSDK_TARGET].cfg.tp_rank];
   s.fwd_seq = e->ws.ar_state;
   s.call_idx = call_idx;
+  s.n_calls = 2 * e->model[SSDK_TARGET].cfg.layers + 1;
   s.n_ranks = e->symm_n;
   s.slot_bytes = e->symm_slot_bytes;
   return s;
@@ -539,9 +555,32 @@ static int enqueue_ar_publish(ssdk_engine* e, Launcher& L, const GemmOut* x, con
   ap.M = M; ap.d = d; ap.n_ranks = e->symm_n; ap.rank = m.cfg.tp_rank;
   for (int r = 0; r < e->symm_n; ++r) ap.peer[r] = e->symm_peer[r];
   ap.slot_bytes = e->symm_slot_bytes;
-  ap.fwd_seq = e->ws.ar_state; ap.call_idx = call_idx;
+  ap.fwd_seq = e->ws.ar_state; ap.call_idx = call_idx; ap.n_calls = 2 * m.cfg.layers + 1;
   const int n8 = M * d / 8;
   return L.go(ar_publish_kernel, dim3(std::max(1, std::min((n8 + 255) / 256, num_sms()))), dim3(256), 0, ap);
+}
+
+// row-parallel GEMM whose epilogue publishes the rank's bf16 result to every peer (EPI_PUBLISH)
+static PublishParams publish_params(ssdk_engine* e, int call_idx) {
+  Model& m = e->model[SSDK_TARGET];
+  PublishParams pb;
+  memset(&pb, 0, sizeof(pb));
+  for (int r = 0; r < e->symm_n; ++r) pb.peer[r] = e->symm_peer[r];
+  pb.fwd_seq = e->ws.ar_state;
+  pb.slot_bytes = e->symm_slot_bytes;
+  pb.call_idx = call_idx;
+  pb.n_calls = 2 * m.cfg.layers + 1;
+  pb.n_ranks = e->symm_n;
+  pb.rank = m.cfg.tp_rank;
+  return pb;
+}
+static bool fused_publish_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("SSDK_FUSED_PUBLISH");
+    v = (s && *s) ? (atoi(s) != 0 ? 1 : 0) : 1;
+  }
+  return v == 1;
 }
 
 static int enqueue_tp_allreduce(ssdk_engine* e, Launcher& L, int S, int M, int N, GemmOut* out) {
@@ -647,12 +686,20 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
                           w.att_lse, w.att_counters, f.B, f.Q, m.H, m.KV, m.hd, bs, mb, scale, TQ, MT, nqt, nsplit));
 
     // ---- output projection (row-parallel) ----
-    CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
+    const bool fuse_pub = use_symm && fused_publish_enabled();
     GemmOut oproj;
-    oproj.dense = nullptr; oproj.partial = w.partials; oproj.S = S; oproj.M = M; oproj.N = m.d;
     bool oproj_symm = false;
     int oproj_idx = 0;
-    if (tp > 1) {
+    if (fuse_pub) {
+      const PublishParams pb = publish_params(e, ar_idx);
+      CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PUBLISH, w.partials, 0, m.d, &S, &pb));
+      oproj_idx = ar_idx++;
+      oproj_symm = true;
+    } else {
+      CKI(enqueue_gemm(e, L, w.attn_out, lw.o, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
+    }
+    oproj.dense = nullptr; oproj.partial = w.partials; oproj.S = S; oproj.M = M; oproj.N = m.d;
+    if (tp > 1 && !fuse_pub) {
       if (use_symm) {
         CKI(enqueue_ar_publish(e, L, &oproj, nullptr, M, m.d, ar_idx));
         oproj_idx = ar_idx++;
@@ -670,19 +717,18 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
     pn.y = w.hidden; pn.residual_out = w.residual; pn.d = m.d;
     CKI(launch_norm(L, M, m.d, pn));
 
-    // ---- MLP: gate|up with fused SiLU*mul when the tile count fills the machine ----
-    const int silu_tiles = (m.ffn + 63) / 64;
-    if (silu_tiles >= num_sms() / 2) {
-      CKI(enqueue_gemm(e, L, w.hidden, lw.gate_up, M, EPI_SILU, w.act, m.ffn, m.ffn, nullptr));
+    // ---- MLP: gate|up with fused SiLU*mul (split-K inside the kernel when the shard is too narrow to fill the machine) ----
+    CKI(enqueue_gemm(e, L, w.hidden, lw.gate_up, M, EPI_SILU, w.act, m.ffn, m.ffn, nullptr));
+    if (fuse_pub) {
+      const PublishParams pb = publish_params(e, ar_idx);
+      CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_PUBLISH, w.partials, 0, m.d, &S, &pb));
+      prev_idx = ar_idx++;
+      prev_symm = true;
     } else {
-      CKI(enqueue_gemm(e, L, w.hidden, lw.gate_up, M, EPI_PARTIAL, w.partials, 0, 2 * m.ffn, &S));
-      GemmOut gu;
-      gu.dense = nullptr; gu.partial = w.partials; gu.S = S; gu.M = M; gu.N = 2 * m.ffn;
-      CKI(L.go(silu_mul_kernel, dim3((M * m.ffn / 8 + 255) / 256), dim3(256), 0, gu, w.act, M, m.ffn));
+      CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
     }
-    CKI(enqueue_gemm(e, L, w.act, lw.down, M, EPI_PARTIAL, w.partials, 0, m.d, &S));
     prev.dense = nullptr; prev.partial = w.partials; prev.S = S; prev.M = M; prev.N = m.d;
-    if (tp > 1) {
+    if (tp > 1 && !fuse_pub) {
       if (use_symm) {
         CKI(enqueue_ar_publish(e, L, &prev, nullptr, M, m.d, ar_idx));
         prev_idx = ar_idx++;
@@ -783,31 +829,51 @@ __global__ void advance_kernel(int32_t* __restrict__ ctx, int64_t* __restrict__ 
 // spec step: K+1 draft forwards -> (K+1)-token target forward -> verify      (enqueue only)
 // ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
-// persistent draft forward (EXPERIMENTAL, SSDK_DRAFT_PERSISTENT=1): one cooperative launch per draft decode forward
+// streaming draft kernel: the K+1 draft forwards + K samplings of a step in ONE cooperative launch (draft_stream.cuh)
+// SSDK_DRAFT_STREAM=0 keeps the kernel-per-op path; SSDK_DRAFT_L2_AHEAD=n requests n further stages per CTA into L2.
 // ------------------------------------------------------------------------------------------
-static bool draft_persistent_enabled() {
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+static bool draft_stream_enabled() {
   static int v = -1;
-  if (v < 0) {
-    const char* s = getenv("SSDK_DRAFT_PERSISTENT");
-    v = (s && atoi(s) != 0) ? 1 : 0;
-  }
+  if (v < 0) v = env_int("SSDK_DRAFT_STREAM", 1) != 0 ? 1 : 0;
   return v == 1;
 }
-static bool draft_persistent_supported(const Model& m, const Fwd& f) {
+constexpr int kMaxDynSmem = 227 * 1024;
+static size_t ds_fixed_smem(const Model& m) {
+  const int G = m.H / m.KV, gmax = G <= 4 ? 4 : 8;
+  const size_t xs = (size_t)std::max(std::max(m.d, m.ffn), m.H * m.hd);
+  const size_t scratch = (size_t)gmax * m.hd + 2 * m.hd + (size_t)kDsWarps * gmax * (m.hd + 2);
+  return (xs + scratch) * 4 + 256;
+}
+static int ds_ring_stages(const Model& m) {
+  const size_t fixed = ds_fixed_smem(m);
+  if (fixed + 3 * (size_t)kDsStageBytes > (size_t)kMaxDynSmem) return 0;
+  return (int)std::min<size_t>(kDsMaxStages, ((size_t)kMaxDynSmem - fixed) / kDsStageBytes);
+}
+static bool ds_k_ok(int K) {
+  if (K < 256 || K > 8192) return false;
+  int R, segs;
+  ds_geometry(K, &R, &segs);
+  return K % (256 * segs) == 0;
+}
+static bool draft_stream_supported(const Model& m, int B) {
   const int G = m.KV ? m.H / m.KV : 0;
-  return f.B == 1 && f.Q == 1 && m.cfg.tp_size == 1 && m.cfg.layers <= kDpMaxLayers && (m.hd == 64 || m.hd == 128) &&
-         G >= 1 && G <= 8 && m.d % 256 == 0 && m.ffn % 256 == 0 && (m.H * m.hd) % 256 == 0;
+  return B == 1 && m.cfg.tp_size == 1 && m.cfg.layers <= kDsMaxLayers && (m.hd == 64 || m.hd == 128) && G >= 1 && G <= 8 &&
+         m.H % m.KV == 0 && ds_k_ok(m.d) && ds_k_ok(m.H * m.hd) && ds_k_ok(m.ffn) && m.d % 8 == 0 && ds_ring_stages(m) >= 3;
 }
 template <int HD, int GMAX>
-static int launch_draft_persistent(Launcher& L, const DpParams& p, size_t smem) {
+static int launch_draft_stream(Launcher& L, const DsParams& p, size_t smem) {
   static bool attr_set = false;
   if (!attr_set) {
-    CK(cudaFuncSetAttribute(draft_forward_persistent_kernel<HD, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(draft_stream_kernel<HD, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(num_sms());
-  cfg.blockDim = dim3(kDpThreads);
+  cfg.blockDim = dim3(kDsThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = L.st;
   cudaLaunchAttribute attr[1];
@@ -815,16 +881,19 @@ static int launch_draft_persistent(Launcher& L, const DpParams& p, size_t smem) 
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, draft_forward_persistent_kernel<HD, GMAX>, p);
-  if (err != cudaSuccess) return fail("persistent draft launch failed: %s", cudaGetErrorString(err));
+  cudaError_t err = cudaLaunchKernelEx(&cfg, draft_stream_kernel<HD, GMAX>, p);
+  if (err != cudaSuccess) return fail("draft stream launch failed: %s", cudaGetErrorString(err));
   L.barrier_op();  // not a PDL primary: the next kernel starts after this grid has drained
   ++L.count;
   return 0;
 }
-static int enqueue_draft_persistent(ssdk_engine* e, Launcher& L, const Fwd& f) {
+// forwards 0 .. n_fwd-1 of the draft on tok_buf[0 ..]; samples tok_buf[f + 1] after every forward but (optionally) the last
+static int enqueue_draft_stream(ssdk_engine* e, Launcher& L, int64_t* tok_buf, int n_fwd, bool skip_last_head,
+                                const int32_t* ctx0, const int32_t* block_table, const float* temp, const uint64_t* dyn,
+                                bf16* logits, int64_t logits_ld) {
   Model& m = e->model[SSDK_DRAFT];
   Workspace& w = e->ws;
-  DpParams p;
+  DsParams p;
   memset(&p, 0, sizeof(p));
   p.d = m.d; p.L = m.cfg.layers; p.H = m.H; p.KV = m.KV; p.ffn = m.ffn; p.vocab = m.cfg.vocab; p.qk_norm = m.cfg.qk_norm;
   p.eps = m.cfg.rms_eps;
@@ -833,29 +902,32 @@ static int enqueue_draft_persistent(ssdk_engine* e, Launcher& L, const Fwd& f) {
   p.k_cache = m.k_cache; p.v_cache = m.v_cache;
   p.cache_layer_stride = (long long)m.num_blocks * e->rt.block_size * m.KV * m.hd;
   p.block_size = e->rt.block_size; p.max_blocks = e->rt.max_blocks_per_seq;
-  p.token = f.ids; p.ctx0 = f.ctx0; p.pos_offset = f.pos_offset; p.block_table = f.block_tables;
-  bf16* v = w.dp_vec;
+  p.tok_buf = tok_buf; p.n_fwd = n_fwd; p.skip_last_head = skip_last_head ? 1 : 0;
+  p.ctx0 = ctx0; p.block_table = block_table;
+  bf16* v = w.ds_vec;
   p.vec_qkv = v; v += align_up((size_t)m.qkv_dim, 8);
   p.vec_o = v; v += m.d;
   p.vec_down = v; v += m.d;
   p.resid0 = v; v += m.d;
   p.resid1 = v; v += m.d;
   p.vec_act = v;
-  p.attn_part = w.dp_attn;
-  p.logits = f.logits_mode ? f.logits_out : nullptr;
-  p.bar_counter = w.dp_sync; p.launch_count = w.dp_sync + 1;
+  p.attn_part = w.ds_attn;
+  p.logits = logits; p.logits_ld = logits_ld;
+  p.temp = temp; p.dyn = dyn;
+  p.samp_partial = w.samp_partial;
+  p.bar_state = w.ds_sync;
+  p.n_stages = ds_ring_stages(m);
+  p.l2_ahead = std::max(0, env_int("SSDK_DRAFT_L2_AHEAD", 0));
   for (int l = 0; l < p.L; ++l) {
     const LayerW& lw = m.layers[l];
-    p.layers[l] = DpLayer{lw.qkv.ptr, lw.o.ptr, lw.gate_up.ptr, lw.down.ptr, lw.input_norm, lw.post_norm, lw.q_norm, lw.k_norm};
+    p.layers[l] = DsLayer{lw.qkv.ptr, lw.o.ptr, lw.gate_up.ptr, lw.down.ptr, lw.input_norm, lw.post_norm, lw.q_norm, lw.k_norm};
   }
   const int G = m.H / m.KV, gmax = G <= 4 ? 4 : 8;
-  const size_t xs = (size_t)std::max(std::max(m.d, m.ffn), m.H * m.hd);
-  const size_t scratch = (size_t)gmax * m.hd + 2 * m.hd + (size_t)kDpWarps * gmax * (m.hd + 2);
-  const size_t smem = (xs + scratch) * 4;
-  if (m.hd == 64 && gmax == 4) return launch_draft_persistent<64, 4>(L, p, smem);
-  if (m.hd == 64 && gmax == 8) return launch_draft_persistent<64, 8>(L, p, smem);
-  if (m.hd == 128 && gmax == 4) return launch_draft_persistent<128, 4>(L, p, smem);
-  return launch_draft_persistent<128, 8>(L, p, smem);
+  const size_t smem = ds_fixed_smem(m) + (size_t)p.n_stages * kDsStageBytes;
+  if (m.hd == 64 && gmax == 4) return launch_draft_stream<64, 4>(L, p, smem);
+  if (m.hd == 64 && gmax == 8) return launch_draft_stream<64, 8>(L, p, smem);
+  if (m.hd == 128 && gmax == 4) return launch_draft_stream<128, 4>(L, p, smem);
+  return launch_draft_stream<128, 8>(L, p, smem);
 }
 
 static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, bool advance) {
@@ -880,7 +952,10 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
   if (tp > 1 && !e->comm) return fail("tensor parallel spec step without a NCCL communicator");
   if (tp_rank == 0 && !drf.present) return fail("rank 0 needs the draft model");
   if (drf.present) CKI(L.go(init_tokens_kernel, dim3(1), dim3(64), 0, (const int64_t*)rec_in, w.tok_buf, B, K + 1));
-  for (int k = 0; k <= K && drf.present; ++k) {
+  const bool stream_draft = drf.present && draft_stream_enabled() && draft_stream_supported(drf, B);
+  if (stream_draft)
+    CKI(enqueue_draft_stream(e, L, w.tok_buf, K + 1, true, ctx, btd, tq, seed_step, w.logits_q, (int64_t)V));
+  for (int k = 0; k <= K && drf.present && !stream_draft; ++k) {
     Fwd f;
     f.which = SSDK_DRAFT; f.B = B; f.Q = 1; f.ids = w.tok_buf + k; f.ids_stride = K + 1;
     f.ctx0 = ctx; f.block_tables = btd; f.pos_offset = k;
@@ -888,8 +963,7 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
     f.logits_mode = (k < K) ? 1 : 0;
     f.logits_out = w.logits_q + (size_t)k * V;
     f.logits_ld = (int64_t)K * V;
-    if (draft_persistent_enabled() && draft_persistent_supported(drf, f)) CKI(enqueue_draft_persistent(e, L, f));
-    else CKI(enqueue_forward(e, L, f));
+    CKI(enqueue_forward(e, L, f));
     if (k < K) {
       SampleParams sp;
       sp.logits = w.logits_q + (size_t)k * V; sp.ld = (int64_t)K * V; sp.temps = tq; sp.V = drf.cfg.vocab;
@@ -974,9 +1048,9 @@ static int get_spec_graph(ssdk_engine* e, int B, bool host_io, cudaStream_t st, 
 static int init_kernel_attrs() {
 #define SSDK_ATTR_G(UN, EP) \
   CK(cudaFuncSetAttribute(gemm_ws_kernel<UN, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<UN>::kSmemBytes));
-  SSDK_ATTR_G(16, EPI_BF16) SSDK_ATTR_G(16, EPI_PARTIAL) SSDK_ATTR_G(16, EPI_SILU)
-  SSDK_ATTR_G(32, EPI_BF16) SSDK_ATTR_G(32, EPI_PARTIAL) SSDK_ATTR_G(32, EPI_SILU)
-  SSDK_ATTR_G(64, EPI_BF16) SSDK_ATTR_G(64, EPI_PARTIAL) SSDK_ATTR_G(64, EPI_SILU)
+  SSDK_ATTR_G(16, EPI_BF16) SSDK_ATTR_G(16, EPI_PARTIAL) SSDK_ATTR_G(16, EPI_SILU) SSDK_ATTR_G(16, EPI_PUBLISH)
+  SSDK_ATTR_G(32, EPI_BF16) SSDK_ATTR_G(32, EPI_PARTIAL) SSDK_ATTR_G(32, EPI_SILU) SSDK_ATTR_G(32, EPI_PUBLISH)
+  SSDK_ATTR_G(64, EPI_BF16) SSDK_ATTR_G(64, EPI_PARTIAL) SSDK_ATTR_G(64, EPI_SILU) SSDK_ATTR_G(64, EPI_PUBLISH)
 #undef SSDK_ATTR_G
 #define SSDK_ATTR_A(HD, MT) \
   CK(cudaFuncSetAttribute(paged_attn_kernel<HD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * kAttChunk * (HD + 8) * 2));

@@ -32,7 +32,23 @@ constexpr int kBlockK = 64;    // bf16 per k-block = 128 B = one swizzle row
 constexpr int kTileRows = 128; // weight rows per CTA = UMMA_M
 constexpr int kGemmThreads = 192;
 
-enum GemmEpi { EPI_BF16 = 0, EPI_PARTIAL = 1, EPI_SILU = 2 };
+enum GemmEpi { EPI_BF16 = 0, EPI_PARTIAL = 1, EPI_SILU = 2, EPI_PUBLISH = 3 };
+
+// EPI_PUBLISH — row-parallel linear + the first half of the one-shot tensor-parallel all-reduce in ONE kernel
+// (layers/linear.py:195-199: y = x W^T, then dist.all_reduce).  Every split-K CTA stores its fp32 partial tile and takes a
+// ticket; the LAST CTA of a tile sums the S partials in the fixed order s = 0..S-1 (bit-identical to the unfused path),
+// rounds to bf16 like the reference's per-rank F.linear output and pushes {2 x bf16, epoch} words straight from its
+// registers into slot[parity][rank] of every rank's NVLink symmetric buffer.  The consumer (add_rmsnorm_kernel with
+// SymmIn) polls the words themselves, so no separate publish kernel, no re-read of the partials by another grid and no
+// kernel boundary sit between the GEMM and the all-reduce.
+constexpr int kPubMaxRanks = 8;
+struct PublishParams {
+  uint8_t* peer[kPubMaxRanks];  // symmetric buffer of every rank (peer-mapped)
+  const unsigned* fwd_seq;      // sequence number of the running target forward (epoch base)
+  unsigned slot_bytes;
+  int call_idx, n_calls;        // static index of this all-reduce inside the forward / all-reduces per forward
+  int n_ranks, rank;
+};
 
 struct GemmParams {
   void* out;          // EPI_BF16/EPI_SILU: bf16 [M, ldo]; EPI_PARTIAL: fp32 [S, M, N]
@@ -43,7 +59,53 @@ struct GemmParams {
   int kb_per_split;   // k-blocks per blockIdx.y
   int tile_rows;      // output columns per tile: 128 (plain) or 64 (silu)
   int hi_row_offset;  // W row offset of the second 64-row half: 64 (plain) or ffn (silu)
+  // in-kernel split-K reduction (EPI_PUBLISH, EPI_SILU with gridDim.y > 1): every split stores its fp32 partial tile and
+  // takes a ticket; the last CTA of a tile sums the S partials in the fixed order s = 0..S-1 and runs the epilogue
+  float* sk_partials;     // fp32 [S, M, sk_width]
+  unsigned* sk_counters;  // [tiles] arrival tickets, zero on entry and on exit
+  int sk_width;           // row width of the partial buffer (N, or 2 * ffn for gate|up)
+  PublishParams pub;      // EPI_PUBLISH only
 };
+
+// Split-K ticket reduction run by the 4 epilogue warps (threads 64..191).  `col` = this thread's column in the partial
+// buffer (< 0: no column).  Returns true in the CTA that arrived last, with r[m] replaced by the sum over all splits.
+template <int UMMA_N>
+SSDK_DEVINL bool splitk_ticket_reduce(uint32_t* r, const GemmParams& p, int col, int tile, int* smem_flag) {
+  const int S = (int)gridDim.y;
+  if (S <= 1) return true;
+  if (col >= 0) {
+    float* out = p.sk_partials + (size_t)blockIdx.y * p.M * p.sk_width;
+#pragma unroll
+    for (int m = 0; m < UMMA_N; ++m)
+      if (m < p.M) out[(size_t)m * p.sk_width + col] = __uint_as_float(r[m]);
+  }
+  __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (threadIdx.x == 64) *smem_flag = (atomicAdd(&p.sk_counters[tile], 1u) == (unsigned)S - 1u) ? 1 : 0;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (*smem_flag == 0) return false;
+  __threadfence();
+  if (threadIdx.x == 64) p.sk_counters[tile] = 0u;  // every CTA of this tile has taken its ticket
+  if (col >= 0) {
+    const size_t stride = (size_t)p.M * p.sk_width;
+#pragma unroll
+    for (int m = 0; m < UMMA_N; ++m) {
+      if (m < p.M) {
+        const float* src = p.sk_partials + (size_t)m * p.sk_width + col;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (q < S && q != (int)blockIdx.y) ? __ldcg(src + (size_t)q * stride) : 0.f;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < S) acc += (q == (int)blockIdx.y) ? __uint_as_float(r[m]) : v[q];
+        r[m] = __float_as_uint(acc);
+      }
+    }
+  }
+  return true;
+}
+
 
 template <int UMMA_N>
 struct GemmCfg {
@@ -66,6 +128,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ int pub_last;
 
   // 128B swizzle needs 1024 B aligned tiles
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -182,8 +245,40 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         for (int m = 0; m < UMMA_N; ++m)
           if (m < p.M) out[(size_t)m * p.N + n] = __uint_as_float(r[m]);
       }
+    } else if (EPI == EPI_PUBLISH) {
+      const PublishParams& pb = p.pub;
+      const int n = row_lo + row;
+      const bool last = splitk_ticket_reduce<UMMA_N>(r, p, n < p.N ? n : -1, tile, &pub_last);
+      if (last) {
+        const unsigned seq = __ldcg(pb.fwd_seq);
+        const unsigned e = symm_epoch_of(seq, pb.call_idx);
+        const size_t slot_off = ((size_t)symm_parity_of(seq, pb.call_idx, pb.n_calls) * kPubMaxRanks + pb.rank) * pb.slot_bytes;
+#pragma unroll
+        for (int m = 0; m < UMMA_N; ++m) {
+          if (m < p.M) {
+            const __nv_bfloat16 mine = f2bf(__uint_as_float(r[m]));
+            const uint32_t bits = (uint32_t)__bfloat16_as_ushort(mine);
+            const uint32_t nb = __shfl_down_sync(0xffffffffu, bits, 1);
+            if ((lane & 1) == 0 && n < p.N) {
+              const uint2 word = make_uint2(bits | (nb << 16), e);
+              const size_t off = slot_off + (((size_t)m * p.N + n) >> 1) * 8;
+#pragma unroll
+              for (int rk = 0; rk < kPubMaxRanks; ++rk)
+                if (rk < pb.n_ranks) st_global_v2_u32(pb.peer[rk] + off, word.x, word.y);  // ONE 8-byte store: data + flag
+            }
+          }
+        }
+      }
     } else {
       // SiLU(gate) * up: rows 0..63 = gate, 64..127 = up of the same 64 output columns.
+      // With split-K (narrow tensor-parallel shards: too few 64-column tiles to fill the machine) the last CTA of a
+      // tile first sums the partial gate / up rows of all splits; the nonlinearity is applied once, on the full sums.
+      {
+        const int j = row & 63;
+        const int ncol = row_lo + j;
+        const int col = ncol < p.N ? (row < 64 ? ncol : p.N + ncol) : -1;
+        if (!splitk_ticket_reduce<UMMA_N>(r, p, col, tile, &pub_last)) goto epilogue_done;
+      }
       // All MMAs have retired (tmem_full), so pipeline stage 0 is free to stage the exchange.
       float* ex = reinterpret_cast<float*>(smem);
       constexpr int LD = UMMA_N + 1;
@@ -206,6 +301,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     }
   }
 
+epilogue_done:
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 64) trace_fine(TRF_GEMM + 1);  // CTA 0's epilogue stored

@@ -22,8 +22,11 @@ static std::vector<T> rd(std::ifstream& f, size_t n) {
 int main(int argc, char** argv) {
   if (argc != 3) return 2;
   std::ifstream f(argv[1], std::ios::binary);
-  auto hdr = rd<int32_t>(f, 6);
-  const int R = hdr[0], M = hdr[1], d = hdr[2], S = hdr[3], n_calls = hdr[4], threads = hdr[5];
+  auto hdr = rd<int32_t>(f, 7);
+  // n_calls all-reduces per forward (odd, like the 2L+1 of a real forward), n_fwd forwards back to back with NO other
+  // cross-rank synchronisation in between; rank `slow` dawdles in the last consumer of every forward
+  const int R = hdr[0], M = hdr[1], d = hdr[2], S = hdr[3], per_fwd = hdr[4], threads = hdr[5], n_fwd = hdr[6];
+  const int n_calls = per_fwd * n_fwd, slow = R - 1;
   const float eps = rd<float>(f, 1)[0];
   auto w = rd<bf16>(f, d);
   auto resid0 = rd<bf16>(f, (size_t)M * d);
@@ -41,6 +44,8 @@ int main(int argc, char** argv) {
     ranks.emplace_back([&, rank] {
       std::mt19937 rng(1234 + rank);
       for (int call = 0; call < n_calls; ++call) {
+        const int idx = call % per_fwd;
+        if (idx == 0 && call > 0) fwd_seq[rank] += 1;  // prep_kernel bumps the forward sequence number
         std::this_thread::sleep_for(std::chrono::microseconds(rng() % 3000));  // skew the ranks against each other
         ssdk::ArPublishParams ap;
         std::memset(&ap, 0, sizeof(ap));
@@ -48,13 +53,14 @@ int main(int argc, char** argv) {
         ap.x.S = S; ap.x.M = M; ap.x.N = d;
         ap.M = M; ap.d = d; ap.n_ranks = R; ap.rank = rank;
         for (int r = 0; r < R; ++r) ap.peer[r] = reinterpret_cast<uint8_t*>(symm[r].data());
-        ap.slot_bytes = slot_bytes; ap.fwd_seq = &fwd_seq[rank]; ap.call_idx = call;
+        ap.slot_bytes = slot_bytes; ap.fwd_seq = &fwd_seq[rank]; ap.call_idx = idx; ap.n_calls = per_fwd;
         emu::launch(ssdk::ar_publish_kernel, ap, std::max(1, std::min((M * d / 8 + 255) / 256, 4)), 256, 0);
         std::this_thread::sleep_for(std::chrono::microseconds(rng() % 2000));
+        if (rank == slow && idx == per_fwd - 1) std::this_thread::sleep_for(std::chrono::milliseconds(30));
         ssdk::NormParams np;
         std::memset(&np, 0, sizeof(np));
         np.symm.base = reinterpret_cast<const uint8_t*>(symm[rank].data());
-        np.symm.fwd_seq = &fwd_seq[rank]; np.symm.no_dep_wait = 1; np.symm.call_idx = call; np.symm.n_ranks = R;
+        np.symm.fwd_seq = &fwd_seq[rank]; np.symm.no_dep_wait = 1; np.symm.call_idx = idx; np.symm.n_calls = per_fwd; np.symm.n_ranks = R;
         np.symm.slot_bytes = slot_bytes;
         np.residual_in = resid[rank].data(); np.residual_out = resid[rank].data(); np.w = w.data(); np.eps = eps;
         np.y = y[rank].data() + (size_t)call * M * d; np.d = d;

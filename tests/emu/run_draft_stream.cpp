@@ -1,9 +1,9 @@
-// Runs the SOURCE of csrc/draft_persistent.cuh on host threads (cuda_emu.h).  TEST INFRASTRUCTURE.
+// Runs the SOURCE of csrc/draft_stream.cuh on host threads (cuda_emu.h).  TEST INFRASTRUCTURE.
 //   run_draft_persistent <input blob> <output blob>
 // blob layout: see tests/test_draft_persistent_emu_cpu.py (the writer).
 #include "cuda_emu.h"
 #define SSDK_HOST_EMU 1
-#include "../../ssd_b200/csrc/draft_persistent.cuh"
+#include "../../ssd_b200/csrc/draft_stream.cuh"
 
 #include <fstream>
 #include <iostream>
@@ -37,9 +37,11 @@ int main(int argc, char** argv) {
   Reader r(argv[1]);
   const int d = r.i32(), L = r.i32(), H = r.i32(), KV = r.i32(), hd = r.i32(), ffn = r.i32(), vocab = r.i32();
   const int qk_norm = r.i32(), block_size = r.i32(), max_blocks = r.i32(), nslots = r.i32(), ctx0 = r.i32();
-  const int n_fwd = r.i32(), grid = r.i32(), max_pos = r.i32();
+  const int n_fwd = r.i32(), grid = r.i32(), max_pos = r.i32(), n_stages = r.i32(), skip_last = r.i32();
   const float eps = r.f32();
-  auto tokens = r.vec<int64_t>(n_fwd);
+  float temp = r.f32();
+  auto rng = r.vec<uint64_t>(2);  // seed, call_base
+  auto tokens = r.vec<int64_t>(1);  // first input token
   auto block_table = r.vec<int32_t>(max_blocks);
   auto embed = r.vec<bf16>((size_t)vocab * d), final_norm = r.vec<bf16>(d), lm_head = r.vec<bf16>((size_t)vocab * d);
   auto rope = r.vec<float>((size_t)max_pos * hd);
@@ -62,11 +64,14 @@ int main(int argc, char** argv) {
   auto kc = r.vec<bf16>(cache_layer * L), vc = r.vec<bf16>(cache_layer * L);
 
   std::vector<bf16> vecs((size_t)qkv_dim + 4 * d + ffn + 64), logits((size_t)n_fwd * vocab);
-  std::vector<float> attn((size_t)H * ssdk::kDpSplits * (hd + 2));
+  std::vector<float> attn((size_t)H * ssdk::kDsSplits * (hd + 2));
+  std::vector<ssdk::ArgMax> partial(grid);
+  std::vector<int64_t> tok_buf(n_fwd + 1, -1);
+  tok_buf[0] = tokens[0];
   unsigned sync[2] = {0, 0};
   int32_t ctx0_dev = ctx0;
 
-  ssdk::DpParams p;
+  ssdk::DsParams p;
   std::memset(&p, 0, sizeof(p));
   p.d = d; p.L = L; p.H = H; p.KV = KV; p.ffn = ffn; p.vocab = vocab; p.qk_norm = qk_norm;
   p.eps = eps;
@@ -75,6 +80,7 @@ int main(int argc, char** argv) {
   p.k_cache = kc.data(); p.v_cache = vc.data();
   p.cache_layer_stride = (long long)cache_layer;
   p.block_size = block_size; p.max_blocks = max_blocks;
+  p.tok_buf = tok_buf.data(); p.n_fwd = n_fwd; p.skip_last_head = skip_last;
   p.ctx0 = &ctx0_dev; p.block_table = block_table.data();
   bf16* v = vecs.data();
   p.vec_qkv = v; v += (qkv_dim + 7) / 8 * 8;
@@ -84,24 +90,29 @@ int main(int argc, char** argv) {
   p.resid1 = v; v += d;
   p.vec_act = v;
   p.attn_part = attn.data();
-  p.bar_counter = &sync[0]; p.launch_count = &sync[1];
+  p.logits = logits.data(); p.logits_ld = vocab;
+  p.temp = &temp; p.dyn = nullptr; p.seed = rng[0]; p.call_base = rng[1];
+  p.samp_partial = partial.data();
+  p.bar_state = sync;
+  p.n_stages = n_stages; p.l2_ahead = 2;
   for (int l = 0; l < L; ++l)
-    p.layers[l] = ssdk::DpLayer{lw[l].qkv.data(), lw[l].o.data(), lw[l].gate_up.data(), lw[l].down.data(),
+    p.layers[l] = ssdk::DsLayer{lw[l].qkv.data(), lw[l].o.data(), lw[l].gate_up.data(), lw[l].down.data(),
                                 lw[l].in_norm.data(), lw[l].post_norm.data(), lw[l].q_norm.data(), lw[l].k_norm.data()};
   const int G = H / KV, gmax = G <= 4 ? 4 : 8;
   const size_t xs = (size_t)std::max(std::max(d, ffn), H * hd);
-  const size_t scratch = (size_t)gmax * hd + 2 * hd + (size_t)ssdk::kDpWarps * gmax * (hd + 2);
-  const size_t smem = (xs + scratch) * 4;
-  for (int j = 0; j < n_fwd; ++j) {
-    p.token = &tokens[j];
-    p.pos_offset = j;
-    p.logits = logits.data() + (size_t)j * vocab;
-    if (hd == 64 && gmax == 4) emu::launch(ssdk::draft_forward_persistent_kernel<64, 4>, p, grid, ssdk::kDpThreads, smem);
-    else if (hd == 64) emu::launch(ssdk::draft_forward_persistent_kernel<64, 8>, p, grid, ssdk::kDpThreads, smem);
-    else if (gmax == 4) emu::launch(ssdk::draft_forward_persistent_kernel<128, 4>, p, grid, ssdk::kDpThreads, smem);
-    else emu::launch(ssdk::draft_forward_persistent_kernel<128, 8>, p, grid, ssdk::kDpThreads, smem);
-    if (sync[1] != (unsigned)(j + 1)) {
-      std::cerr << "launch counter not bumped\n";
+  const size_t scratch = (size_t)gmax * hd + 2 * hd + (size_t)ssdk::kDsWarps * gmax * (hd + 2);
+  const size_t smem = (xs + scratch) * 4 + 256 + (size_t)n_stages * ssdk::kDsStageBytes;
+  // two launches on the same barrier state: the generation-based barrier must carry over
+  for (int rep = 0; rep < 2; ++rep) {
+    if (rep == 1) {  // second launch: same inputs again (KV rows are simply rewritten with the same values)
+      std::fill(tok_buf.begin() + 1, tok_buf.end(), -1);
+    }
+    if (hd == 64 && gmax == 4) emu::launch(ssdk::draft_stream_kernel<64, 4>, p, grid, ssdk::kDsThreads, smem);
+    else if (hd == 64) emu::launch(ssdk::draft_stream_kernel<64, 8>, p, grid, ssdk::kDsThreads, smem);
+    else if (gmax == 4) emu::launch(ssdk::draft_stream_kernel<128, 4>, p, grid, ssdk::kDsThreads, smem);
+    else emu::launch(ssdk::draft_stream_kernel<128, 8>, p, grid, ssdk::kDsThreads, smem);
+    if (sync[0] != 0) {
+      std::cerr << "barrier arrival count not back to zero\n";
       return 3;
     }
   }
@@ -109,5 +120,6 @@ int main(int argc, char** argv) {
   o.write(reinterpret_cast<const char*>(logits.data()), (std::streamsize)(logits.size() * 2));
   o.write(reinterpret_cast<const char*>(kc.data()), (std::streamsize)(kc.size() * 2));
   o.write(reinterpret_cast<const char*>(vc.data()), (std::streamsize)(vc.size() * 2));
+  o.write(reinterpret_cast<const char*>(tok_buf.data()), (std::streamsize)(tok_buf.size() * 8));
   return 0;
 }

@@ -1,7 +1,9 @@
 """The one-shot all-reduce of the tensor-parallel path — `ar_publish_kernel` + the flag-polling input of
 `add_rmsnorm_kernel` (csrc/elementwise.cuh) — executed from SOURCE for 2 and 8 emulated ranks that share host memory the
 way peer-mapped symmetric buffers share HBM (tests/emu/run_allreduce.cpp).  Ranks are skewed against each other with
-random delays, five consecutive all-reduces reuse the two parity slots, and every rank must produce
+random delays, three forwards of five all-reduces each (an ODD count per forward, like the 2L+1 of the real model, with the
+last rank dawdling in the last consumer of every forward — the slot-reuse case across forwards of ADVICE r1 #2) reuse the
+two parity slots, and every rank must produce
 bf16( sum over ranks, in rank order, of that rank's bf16-rounded split-K reduction ) -> residual add -> RMSNorm,
 bit-identically on all ranks.  Covers the 1-slice and the 2-slice norm instantiations."""
 import os
@@ -37,13 +39,14 @@ def _u16(t):
 def test_one_shot_allreduce_source_on_emulated_ranks(tmp_path, R, M, d, S, threads):
     _build()
     g = torch.Generator().manual_seed(R * 1000 + d)
-    n_calls, eps = 5, 1e-5
+    per_fwd, n_fwd, eps = 5, 3, 1e-5
+    n_calls = per_fwd * n_fwd
     w = (1.0 + 0.1 * torch.randn(d, generator=g)).to(BF)
     resid = torch.randn(M, d, generator=g).to(BF)
     partials = torch.randn(R, n_calls, S, M, d, generator=g) * 0.5
     inp, out = tmp_path / "ar.in", tmp_path / "ar.out"
     with open(inp, "wb") as f:
-        np.array([R, M, d, S, n_calls, threads], dtype=np.int32).tofile(f)
+        np.array([R, M, d, S, per_fwd, threads, n_fwd], dtype=np.int32).tofile(f)
         np.array([eps], dtype=np.float32).tofile(f)
         _u16(w).tofile(f)
         _u16(resid).tofile(f)
