@@ -341,6 +341,27 @@ SSDK_DEVINL uint4 ld_nc_v4_evict_first(const void* p) {
                : "l"(p), "l"(kEvictFirst));
   return r;
 }
+// fetch-add with acquire-release semantics at device scope (tickets, device-wide barriers): orders this thread's earlier
+// writes before the add and its later reads after it, without a separate fence
+SSDK_DEVINL unsigned atom_add_acq_rel_gpu(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+// cheap device-wide barrier primitives: a release-add without a return value (the arriving thread does not wait for the
+// L2 round trip), a relaxed polling load (no L1 invalidation per poll) and one acquire fence once the poll has succeeded
+SSDK_DEVINL void red_add_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+SSDK_DEVINL unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+SSDK_DEVINL void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+SSDK_DEVINL void st_relaxed_gpu_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // acquire load at device scope (flag / counter polling)
 SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -368,6 +389,14 @@ SSDK_DEVINL unsigned ld_acquire_u32(const unsigned* p) {
   std::this_thread::yield();
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 }
+SSDK_DEVINL unsigned atom_add_acq_rel_gpu(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_ACQ_REL); }
+SSDK_DEVINL void red_add_release_gpu_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
+SSDK_DEVINL unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  std::this_thread::yield();
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+}
+SSDK_DEVINL void fence_acq_rel_gpu() { std::atomic_thread_fence(std::memory_order_acq_rel); }
+SSDK_DEVINL void st_relaxed_gpu_u32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 SSDK_DEVINL void prefetch_l2(const void*) {}
 // mbarrier + bulk copy stand-ins: one 64-bit word = {phase bit 63 | pending arrivals 32..47 | init count 48..62 | tx bytes 0..31},
 // updated under one global lock (test infrastructure; the bulk copy is a synchronous memcpy by the issuing thread)
@@ -388,6 +417,13 @@ SSDK_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   std::lock_guard<std::mutex> g(emu_mbar_mu());
   uint64_t w = *bar;
   w = (w & ~0xFFFFFFFFull) | (uint32_t)((uint32_t)w + bytes);
+  w -= (1ull << 32);
+  emu_mbar_settle(w);
+  *bar = w;
+}
+SSDK_DEVINL void mbar_arrive(uint64_t* bar) {
+  std::lock_guard<std::mutex> g(emu_mbar_mu());
+  uint64_t w = *bar;
   w -= (1ull << 32);
   emu_mbar_settle(w);
   *bar = w;

@@ -2,20 +2,25 @@
 // K+1 single-token draft forwards + K samplings) as ONE persistent kernel, batch 1.
 //
 // Why: the 1B draft streams 2.47 GB per forward (0.376 ms at the measured HBM peak) but the kernel-per-op path needs
-// 0.79 ms — nine kernel boundaries per layer, during each of which HBM idles (profiles/r01_small_kernels.md).  A first
-// persistent kernel (round 1, five device-wide barriers per layer, weights read straight from global memory) measured
-// 0.85 ms on hardware: a barrier costs as much as a boundary, and HBM still idles at every one of them
-// (profiles/r02_draft_persistent.md).  The weights, however, do not depend on the activations.  So here every CTA
-// (one per SM) streams ITS share of every matrix, in program order and without ever waiting for a phase, through a ring
-// of 32 KB shared-memory stages fed by bulk async copies (cp.async.bulk global->shared, mbarrier completion, L2
-// evict-first): while the CTAs meet at a barrier or recompute a norm, the ring (148 x 160 KB = 23 MB on chip) fills
-// with the NEXT phases' weights, optionally backed by an L2 prefetch window beyond it.  Consumption is plain CUDA-core
-// GEMV from shared memory (one token: 1 FMA per weight element; 0.4 us of shared-memory time per 0.73 us of HBM time).
+// 0.79 ms — nine kernel boundaries per layer, during each of which HBM idles (profiles/r01_small_kernels.md).  The weights
+// do not depend on the activations, so here every CTA (one per SM) streams ITS share of every matrix, in program order
+// and without ever waiting for a phase, through a ring of 32 KB shared-memory slots:
+//   * a PRODUCER warp requests slot after slot with bulk async copies (cp.async.bulk global -> shared, mbarrier
+//     transaction counts, L2 evict-first) as soon as the consumers release them — across phase and layer boundaries, so
+//     while the CTAs meet at a device-wide barrier or recompute a norm the ring (148 x 160 KB = 23 MB on chip) fills with
+//     the NEXT phases' weights;
+//   * 8 CONSUMER warps run the phases.  A projection at one token is a GEMV: each warp keeps its 64-float slice of x in
+//     registers for the whole phase and owns whole rows (K <= 2048: no cross-warp traffic at all), reads 16 bytes per
+//     lane per step from the slot (conflict-free), and releases the slot with one mbarrier arrive per warp.
+// History (profiles/r02_draft_stream.md): persistent kernel with weights read straight from global memory 0.85 ms per
+// forward; first ring version (thread 0 issuing the copies between block-wide barriers, x read from shared memory)
+// 1.05-1.15 ms: the consume loop, not HBM, was the bottleneck (1.2 us per 32 KB slot against 0.73 us of HBM time).
 //
-// Program order per forward (same five phases per layer as the reference's decoder layer, models/llama3.py:185-199):
+// Program order per forward (the five dependent stages of the reference's decoder layer, models/llama3.py:185-199):
 //   A  [residual add + input RMSNorm, recomputed by every CTA] -> q|k|v rows
-//   B  q/k head norm + RoPE + KV store + split-KV attention for (kv head, split) units
-//   C  [merge of the split partials, every CTA] -> o-proj rows
+//   B  q/k head norm + RoPE + KV store + split-KV attention for (kv head, split) units; the last split of a kv head to
+//      finish merges the partials into the attention output vector
+//   C  o-proj rows
 //   D  [residual add + post-attention RMSNorm, every CTA] -> gate|up row pairs + SiLU*mul
 //   E  down-proj rows
 // then final norm -> lm_head rows -> in-kernel sampling (greedy argmax over the bf16 logits, lowest index wins, or the
@@ -24,21 +29,25 @@
 // Rounding points are the reference's (SURVEY §8a checklist 1-4): every linear output, the residual, the norm output, q/k
 // after RoPE and the attention output are rounded to bf16; accumulation is fp32.
 //
-// Matrix rows are dealt to CTAs in stages of R consecutive rows (R * K * 2 bytes <= 32 KB): stage s of a matrix belongs to
-// CTA s mod #CTAs, and a stage is ONE contiguous bulk copy (two for gate|up: R/2 gate rows + the R/2 matching up rows).
-// Inside a stage the 8 warps split (row, K-segment) units: K <= 2048: 8 rows x 1 segment, K <= 4096: 4 x 2, K <= 8192: 2 x 4.
+// Jobs: rows are dealt to CTAs in jobs of consecutive rows; job s of a matrix belongs to CTA s mod #CTAs.
+//   K <= 2048  : 8 rows = one slot, ONE contiguous bulk copy; warp w owns row w.
+//   gate|up    : 8 (gate, up) row pairs = two slots (8 gate rows | the 8 matching up rows); warp w owns pair w.
+//   K >  2048  : R = 4 (K <= 4096) or 2 (K <= 8192) rows = one slot; the 8 warps split (row, K-segment) units and combine
+//                their partial sums in a fixed order through shared memory.
 #pragma once
 #include "common.cuh"
 #include "sampling.cuh"
 
 namespace ssdk {
 
-constexpr int kDsThreads = 256;
-constexpr int kDsWarps = kDsThreads / 32;
+constexpr int kDsConsumers = 256;                 // threads 0..255: 8 consumer warps
+constexpr int kDsWarps = kDsConsumers / 32;
+constexpr int kDsThreads = kDsConsumers + 32;     // + the producer warp
 constexpr int kDsMaxLayers = 32;
 constexpr int kDsSplits = 8;          // KV splits per kv head in phase B
-constexpr int kDsStageBytes = 32768;  // one ring stage
-constexpr int kDsMaxStages = 6;
+constexpr int kDsSlotBytes = 32768;   // one ring slot
+constexpr int kDsMaxSlots = 6;
+constexpr int kDsMaxSteps = 8;        // 256-column steps per K segment (segment <= 2048 columns)
 
 struct DsLayer {
   const __nv_bfloat16 *qkv, *o, *gate_up, *down, *in_norm, *post_norm, *q_norm, *k_norm;
@@ -57,7 +66,7 @@ struct DsParams {
   int skip_last_head;            // 1: the last forward runs without lm_head / sampling (it only writes KV)
   const int32_t* ctx0;           // tokens in the cache before the first forward
   const int32_t* block_table;    // [max_blocks]
-  __nv_bfloat16 *vec_qkv, *vec_o, *vec_act, *vec_down, *resid0, *resid1;
+  __nv_bfloat16 *vec_qkv, *vec_attn, *vec_o, *vec_act, *vec_down, *resid0, *resid1;
   float* attn_part;              // [H][kDsSplits][hd + 2]: o | m | l
   __nv_bfloat16* logits;         // row f at logits + f * logits_ld (may be null: no logits kept)
   long long logits_ld;
@@ -65,94 +74,103 @@ struct DsParams {
   const uint64_t* dyn;           // optional device {seed, step}: call_id = step * 16 + f
   uint64_t seed, call_base;      // used when dyn == nullptr: call_id = call_base + f
   ArgMax* samp_partial;          // [#CTAs]
-  unsigned* bar_state;           // [0] arrivals, [1] generation (both zero before the first launch ever)
-  int n_stages;                  // ring depth (3 .. kDsMaxStages)
-  int l2_ahead;                  // stages requested into L2 beyond the ring (0 = off)
+  unsigned* bar_state;           // one 64-bit arrival counter (8-byte aligned), only ever grows; zero before the first launch
+  unsigned* attn_ticket;         // [KV] arrival tickets of the split-KV units, zero between phases
+  int n_slots;                   // ring depth (3 .. kDsMaxSlots)
   DsLayer layers[kDsMaxLayers];
 };
 
+// consumer-only block barrier (the producer warp runs on its own)
+SSDK_DEVINL void ds_sync() {
+#ifdef SSDK_HOST_EMU
+  ::emu::named_barrier(1, kDsConsumers);
+#else
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
-// device-wide barrier, generation based (no per-launch bookkeeping): the last arriver resets the arrival count and bumps
-// the generation, everybody else polls the generation.  Every CTA reads the generation before its first arrival, i.e.
-// before the first barrier of the launch can complete.
+// device-wide barrier of the consumers: ONE 64-bit arrival counter that only ever grows.  Barrier number n of a launch
+// is complete when the counter reaches base + n * #CTAs, where base = the counter rounded down to a multiple of #CTAs at
+// kernel start (every launch performs whole barriers, and the first barrier of a launch cannot complete before this CTA
+// has arrived, so every CTA computes the same base).  Arrival = one release-add without a return value; waiting = relaxed
+// polling loads + one acquire fence at the end.  (A first version — acq_rel fetch-adds for arrival, counter reset and
+// generation bump, acquire loads for polling — compiled to MEMBAR.ALL.GPU + ATOMG + CCTL.IVALL three times in a row on the
+// last arriver and an L1 invalidation per poll: 2.9 us per barrier, 15 us per layer; profiles/r02_draft_stream.md.)
 // ---------------------------------------------------------------------------------------------
 struct DsGridBar {
-  unsigned* state;
-  unsigned gen;
+  unsigned long long* counter;
+  unsigned long long target;
   __device__ void init() {
-    if (threadIdx.x == 0) gen = ld_acquire_u32(state + 1);
+    if (threadIdx.x == 0) {
+      const unsigned long long c = ld_relaxed_gpu_u64(counter);
+      target = c - c % (unsigned long long)gridDim.x;
+    }
   }
   __device__ void sync() {
-    __syncthreads();
+    ds_sync();  // every consumer thread's writes of this phase are ordered before thread 0's release
     if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned old = atomicAdd(state, 1u);
-      if (old == gridDim.x - 1) {
-        atomicAdd(state, 0u - gridDim.x);  // back to zero (atomic: nobody else touches it until the generation moves)
-        __threadfence();
-        atomicAdd(state + 1, 1u);
-      } else {
-        const long long t0 = clock64();
-        while (ld_acquire_u32(state + 1) == gen) {
-          if (clock64() - t0 > 4000000000LL) __trap();  // a CTA never arrived: fail loudly instead of hanging the GPU
-        }
+      target += (unsigned long long)gridDim.x;
+      red_add_release_gpu_u64(counter, 1ull);
+      const long long t0 = clock64();
+      while (ld_relaxed_gpu_u64(counter) < target) {
+        if (clock64() - t0 > 4000000000LL) __trap();  // a CTA never arrived: fail loudly instead of hanging the GPU
       }
-      gen += 1u;
-      __threadfence();
+      fence_acq_rel_gpu();
     }
-    __syncthreads();
+    ds_sync();
   }
 };
 
 SSDK_DEVINL uint4 ds_ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 SSDK_DEVINL float2 ds_bf2(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w)); }
 
+// timeline marks of the second forward of a launch (CTA 0, thread 0; only when ssdk_debug_trace is on): ids 64 + point
+SSDK_DEVINL void ds_mark(int f, int point) {
+  if (f == 1 && threadIdx.x == 0) trace_mark(64 + point);
+}
+
 // ---------------------------------------------------------------------------------------------
 // matrix geometry and the per-CTA job sequence
 // ---------------------------------------------------------------------------------------------
 enum { DS_QKV = 0, DS_O = 1, DS_GU = 2, DS_DOWN = 3, DS_HEAD = 4 };
-struct DsMat {
-  const __nv_bfloat16* w;
-  int K;      // row length
-  int rows;   // output rows (gate|up: pairs)
-  int R;      // rows per stage (gate|up: R / 2 pairs)
-  int segs;   // K segments per row: R * segs == 8 warps
-  int pair;   // 1: gate|up
+enum { DS_PLAIN = 0, DS_PAIR = 1, DS_SPLIT = 2 };
+struct DsGeom {
+  int K;     // row length
+  int rows;  // output rows (gate|up: pairs)
+  int kind;  // DS_PLAIN / DS_PAIR / DS_SPLIT
+  int rpj;   // rows (pairs) per job
+  int segs;  // K segments per row (DS_SPLIT; 1 otherwise)
+  int nj;    // jobs of the matrix
 };
-__host__ SSDK_DEVINL void ds_geometry(int K, int* R, int* segs) {
-  *R = K <= 2048 ? 8 : (K <= 4096 ? 4 : 2);
-  *segs = kDsWarps / *R;
-}
-template <int HD>
-SSDK_DEVINL DsMat ds_mat(const DsParams& p, int l, int m) {
-  DsMat t;
-  t.pair = 0;
-  const int lc = l < p.L ? l : 0;
-  switch (m) {
-    case DS_QKV: t.w = p.layers[lc].qkv; t.K = p.d; t.rows = (p.H + 2 * p.KV) * HD; break;
-    case DS_O: t.w = p.layers[lc].o; t.K = p.H * HD; t.rows = p.d; break;
-    case DS_GU: t.w = p.layers[lc].gate_up; t.K = p.d; t.rows = p.ffn; t.pair = 1; break;
-    case DS_DOWN: t.w = p.layers[lc].down; t.K = p.ffn; t.rows = p.d; break;
-    default: t.w = p.lm_head; t.K = p.d; t.rows = p.vocab; break;
+__host__ SSDK_DEVINL bool ds_geometry(int K, int rows, bool pair, DsGeom* g) {
+  g->K = K; g->rows = rows; g->segs = 1;
+  if (K < 256 || K > 8192 || (K % 256) != 0) return false;
+  if (pair) {
+    if (K > 2048) return false;  // a pair job is 8 gate rows + 8 up rows in two slots
+    g->kind = DS_PAIR; g->rpj = 8;
+  } else if (K <= 2048) {
+    g->kind = DS_PLAIN; g->rpj = 8;
+  } else {
+    g->kind = DS_SPLIT; g->rpj = K <= 4096 ? 4 : 2; g->segs = kDsWarps / g->rpj;
+    if ((K % (256 * g->segs)) != 0) return false;
   }
-  ds_geometry(t.K, &t.R, &t.segs);
-  return t;
-}
-SSDK_DEVINL int ds_rows_per_stage(const DsMat& t) { return t.pair ? t.R / 2 : t.R; }
-SSDK_DEVINL int ds_num_stages(const DsMat& t) {
-  const int r = ds_rows_per_stage(t);
-  return (t.rows + r - 1) / r;
+  g->nj = (rows + g->rpj - 1) / g->rpj;
+  return true;
 }
 SSDK_DEVINL bool ds_has_head(const DsParams& p, int f) { return !(p.skip_last_head && f == p.n_fwd - 1); }
+SSDK_DEVINL const __nv_bfloat16* ds_weight(const DsParams& p, int l, int m) {
+  const DsLayer& lw = p.layers[l < p.L ? l : 0];
+  return m == DS_QKV ? lw.qkv : (m == DS_O ? lw.o : (m == DS_GU ? lw.gate_up : (m == DS_DOWN ? lw.down : p.lm_head)));
+}
 
-// position in the program: forward f, layer l (l == L: the lm_head), matrix m, stage s (s = CTA, CTA + #CTAs, ...)
+// position in the program: forward f, layer l (l == L: the lm_head), matrix m, job s (s = CTA, CTA + #CTAs, ...)
 struct DsCursor {
   int f, l, m, s;
   bool valid;
 };
-template <int HD>
-SSDK_DEVINL void ds_cursor_settle(const DsParams& p, DsCursor& c) {  // skip matrices in which this CTA has no stage left
-  while (c.valid && c.s >= ds_num_stages(ds_mat<HD>(p, c.l, c.m))) {
+SSDK_DEVINL void ds_cursor_settle(const DsParams& p, const DsGeom* geom, DsCursor& c) {  // skip matrices without a job left
+  while (c.valid && c.s >= geom[c.m].nj) {
     c.s = (int)blockIdx.x;
     if (c.m == DS_HEAD) {
       c.f++; c.l = 0; c.m = DS_QKV;
@@ -168,90 +186,90 @@ SSDK_DEVINL void ds_cursor_settle(const DsParams& p, DsCursor& c) {  // skip mat
     if (c.f >= p.n_fwd) c.valid = false;
   }
 }
-template <int HD>
-SSDK_DEVINL void ds_cursor_init(const DsParams& p, DsCursor& c) {
+
+// the producer: one lane walks the job sequence of this CTA and refills slots as the consumers release them
+SSDK_DEVINL void ds_producer(const DsParams& p, const DsGeom* geom, uint8_t* ring, uint64_t* full, uint64_t* empty) {
+  DsCursor c;
   c.f = 0; c.l = 0; c.m = DS_QKV; c.s = (int)blockIdx.x; c.valid = p.n_fwd > 0;
-  ds_cursor_settle<HD>(p, c);
-}
-template <int HD>
-SSDK_DEVINL void ds_cursor_advance(const DsParams& p, DsCursor& c) {
-  c.s += (int)gridDim.x;
-  ds_cursor_settle<HD>(p, c);
-}
-// (source, bytes) of a job: one contiguous run of rows, two for gate|up (gate rows, then the matching up rows)
-struct DsJob {
-  const __nv_bfloat16 *src0, *src1;
-  unsigned bytes0, bytes1, off1;
-};
-template <int HD>
-SSDK_DEVINL DsJob ds_job(const DsParams& p, const DsCursor& c) {
-  const DsMat t = ds_mat<HD>(p, c.l, c.m);
-  const int r = ds_rows_per_stage(t);
-  const int n = min(r, t.rows - c.s * r);
-  DsJob j;
-  j.src0 = t.w + (size_t)c.s * r * t.K;
-  j.bytes0 = (unsigned)n * (unsigned)t.K * 2u;
-  j.src1 = nullptr; j.bytes1 = 0; j.off1 = 0;
-  if (t.pair) {
-    j.src1 = t.w + ((size_t)t.rows + (size_t)c.s * r) * t.K;
-    j.bytes1 = j.bytes0;
-    j.off1 = (unsigned)r * (unsigned)t.K * 2u;
+  ds_cursor_settle(p, geom, c);
+  unsigned n = 0;  // slots requested so far
+  const unsigned S = (unsigned)p.n_slots;
+  while (c.valid) {
+    const DsGeom g = geom[c.m];
+    const __nv_bfloat16* w = ds_weight(p, c.l, c.m);
+    const int rows = min(g.rpj, g.rows - c.s * g.rpj);
+    const unsigned bytes = (unsigned)rows * (unsigned)g.K * 2u;
+    const int parts = g.kind == DS_PAIR ? 2 : 1;
+    for (int q = 0; q < parts; ++q) {
+      const unsigned slot = n % S, round = n / S;
+      mbar_wait(&empty[slot], (round & 1u) ^ 1u);  // a fresh barrier passes the first round at once
+      mbar_arrive_expect_tx(&full[slot], bytes);
+      const __nv_bfloat16* src = w + ((size_t)(q ? g.rows : 0) + (size_t)c.s * g.rpj) * g.K;
+      bulk_load_g2s(ring + (size_t)slot * kDsSlotBytes, src, bytes, &full[slot]);
+      ++n;
+    }
+    c.s += (int)gridDim.x;
+    if (c.s >= g.nj) ds_cursor_settle(p, geom, c);
   }
-  return j;
 }
 
 // ---------------------------------------------------------------------------------------------
-// the ring: stage `slot` is refilled by thread 0 right after the block has finished reading it
+// consumers
 // ---------------------------------------------------------------------------------------------
 struct DsRing {
   uint8_t* base;
-  uint64_t* full;     // [n_stages] mbarriers (count 1 + transaction bytes)
-  int n_stages;
-  unsigned consumed;  // jobs consumed so far (uniform over the block)
-  DsCursor issue;     // thread 0 only: next job to request into shared memory
-  DsCursor ahead;     // thread 0 only: next job to request into L2
+  uint64_t *full, *empty;
+  unsigned n_slots;
+  unsigned taken;  // slots consumed so far (uniform over the consumers)
 };
-template <int HD>
-SSDK_DEVINL void ds_issue(const DsParams& p, DsRing& r, int slot) {  // thread 0
-  if (!r.issue.valid) return;
-  const DsJob j = ds_job<HD>(p, r.issue);
-  uint8_t* dst = r.base + (size_t)slot * kDsStageBytes;
-  mbar_arrive_expect_tx(&r.full[slot], j.bytes0 + j.bytes1);
-  bulk_load_g2s(dst, j.src0, j.bytes0, &r.full[slot]);
-  if (j.bytes1) bulk_load_g2s(dst + j.off1, j.src1, j.bytes1, &r.full[slot]);
-  ds_cursor_advance<HD>(p, r.issue);
-  if (p.l2_ahead > 0 && r.ahead.valid) {
-    const DsJob a = ds_job<HD>(p, r.ahead);
-    bulk_prefetch_l2(a.src0, a.bytes0);
-    if (a.bytes1) bulk_prefetch_l2(a.src1, a.bytes1);
-    ds_cursor_advance<HD>(p, r.ahead);
-  }
+SSDK_DEVINL const uint8_t* ds_acquire(DsRing& r, unsigned k) {  // wait for the k-th slot after `taken`
+  const unsigned n = r.taken + k, slot = n % r.n_slots;
+  mbar_wait(&r.full[slot], (n / r.n_slots) & 1u);
+  return r.base + (size_t)slot * kDsSlotBytes;
+}
+SSDK_DEVINL void ds_release(DsRing& r, unsigned k, int lane) {  // one arrive per consumer warp, after its last read
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&r.empty[(r.taken + k) % r.n_slots]);
 }
 
-// partial dot of one row segment held in shared memory with the matching slice of x (fp32, shared memory)
-SSDK_DEVINL float ds_dot_seg(const uint8_t* wseg, const float* xseg, int len, int lane) {
+// x stays in REGISTERS for a whole phase: a warp always works on the same K segment (<= 2048 columns), i.e. lane owns the
+// 8 columns [256 j + 8 lane, +8) of every 256-column step j < 8 — 64 floats
+SSDK_DEVINL void ds_load_x(const float* xseg, int steps, int lane, float (&xr)[kDsMaxSteps][8]) {
+#pragma unroll
+  for (int j = 0; j < kDsMaxSteps; ++j) {
+    if (j < steps) {
+      const float4 a = *reinterpret_cast<const float4*>(xseg + j * 256 + lane * 8);
+      const float4 b = *reinterpret_cast<const float4*>(xseg + j * 256 + lane * 8 + 4);
+      xr[j][0] = a.x; xr[j][1] = a.y; xr[j][2] = a.z; xr[j][3] = a.w;
+      xr[j][4] = b.x; xr[j][5] = b.y; xr[j][6] = b.z; xr[j][7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xr[j][e] = 0.f;
+    }
+  }
+}
+// dot of one row segment held in shared memory (16 bytes per lane per step, conflict-free) with x in registers
+SSDK_DEVINL float ds_dot_seg(const uint8_t* wseg, int steps, int lane, const float (&xr)[kDsMaxSteps][8]) {
   const uint4* wp = reinterpret_cast<const uint4*>(wseg) + lane;
-  const float* xp = xseg + lane * 8;
-  float a0 = 0.f, a1 = 0.f;
-  const int steps = len >> 8;  // 256 elements per step
-#pragma unroll 4
-  for (int j = 0; j < steps; ++j) {
-    const uint4 w = wp[j * 32];
-    const float4 xa = *reinterpret_cast<const float4*>(xp + j * 256);
-    const float4 xb = *reinterpret_cast<const float4*>(xp + j * 256 + 4);
-    float2 f = ds_bf2(w.x);
-    a0 = fmaf(f.x, xa.x, a0); a1 = fmaf(f.y, xa.y, a1);
-    f = ds_bf2(w.y);
-    a0 = fmaf(f.x, xa.z, a0); a1 = fmaf(f.y, xa.w, a1);
-    f = ds_bf2(w.z);
-    a0 = fmaf(f.x, xb.x, a0); a1 = fmaf(f.y, xb.y, a1);
-    f = ds_bf2(w.w);
-    a0 = fmaf(f.x, xb.z, a0); a1 = fmaf(f.y, xb.w, a1);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kDsMaxSteps; ++j) {
+    if (j < steps) {
+      const uint4 w = wp[j * 32];
+      float2 f = ds_bf2(w.x);
+      a0 = fmaf(f.x, xr[j][0], a0); a1 = fmaf(f.y, xr[j][1], a1);
+      f = ds_bf2(w.y);
+      a2 = fmaf(f.x, xr[j][2], a2); a3 = fmaf(f.y, xr[j][3], a3);
+      f = ds_bf2(w.z);
+      a0 = fmaf(f.x, xr[j][4], a0); a1 = fmaf(f.y, xr[j][5], a1);
+      f = ds_bf2(w.w);
+      a2 = fmaf(f.x, xr[j][6], a2); a3 = fmaf(f.y, xr[j][7], a3);
+    }
   }
-  return warp_sum(a0 + a1);
+  return warp_sum((a0 + a1) + (a2 + a3));
 }
 
-// sampling state of the lm_head phase (threads 0 .. R-1 of warp 0 each follow their own rows)
+// sampling state of the lm_head phase (lane 0 of every consumer warp follows its own rows)
 struct DsSample {
   bool greedy;
   float invT;
@@ -266,54 +284,96 @@ SSDK_DEVINL float ds_score(const DsSample& s, float logit, int idx) {
   return logit * s.invT - __logf(e);
 }
 
-// consume this CTA's stages of matrix (l, m).  MODE 0: y[row] = bf16(W[row] . x); MODE 1: gate|up pairs ->
-// act[i] = bf16(silu(bf16 g) * bf16 u) (layers/activation.py:11-14); MODE 2: lm_head rows -> logits + running argmax.
-template <int HD, int MODE>
-SSDK_DEVINL void ds_consume(const DsParams& p, DsRing& ring, int l, int m, const float* xs, float* res,
-                            __nv_bfloat16* y, DsSample* smp) {
-  const DsMat t = ds_mat<HD>(p, l, m);
-  const int ns = ds_num_stages(t);
+// rows of a K <= 2048 matrix: y[row] = bf16(W[row] . x)   (HEAD: logits + the warp's running best score)
+template <bool HEAD>
+SSDK_DEVINL void ds_consume_plain(DsRing& ring, const DsGeom& g, const float* xs, __nv_bfloat16* y, DsSample* smp) {
+  if ((int)blockIdx.x >= g.nj) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_in_stage = warp / t.segs, seg = warp - row_in_stage * t.segs;
-  const int seg_len = t.K / t.segs;
-  const int rps = ds_rows_per_stage(t);
-  for (int s = (int)blockIdx.x; s < ns; s += (int)gridDim.x) {
-    const int slot = (int)(ring.consumed % (unsigned)ring.n_stages);
-    const uint32_t parity = (ring.consumed / (unsigned)ring.n_stages) & 1u;
-    mbar_wait(&ring.full[slot], parity);
-    const uint8_t* st = ring.base + (size_t)slot * kDsStageBytes;
-    const float acc = ds_dot_seg(st + ((size_t)row_in_stage * t.K + (size_t)seg * seg_len) * 2, xs + seg * seg_len, seg_len, lane);
-    float* rb = res + (ring.consumed & 1u) * kDsWarps;
-    if (lane == 0) rb[warp] = acc;
-    __syncthreads();  // the stage has been read by every warp; the partial sums are visible
-    if (threadIdx.x == 0) ds_issue<HD>(p, ring, slot);
-    if ((int)threadIdx.x < rps) {
-      const int row = s * rps + (int)threadIdx.x;
-      if (row < t.rows) {
-        if (MODE == 1) {
-          float g = 0.f, u = 0.f;
-          for (int q = 0; q < t.segs; ++q) {
-            g += rb[(int)threadIdx.x * t.segs + q];
-            u += rb[(rps + (int)threadIdx.x) * t.segs + q];
-          }
-          g = bf16_round(g);
-          u = bf16_round(u);
-          y[row] = f2bf((g / (1.0f + __expf(-g))) * u);
-        } else {
-          float v = 0.f;
-          for (int q = 0; q < t.segs; ++q) v += rb[(int)threadIdx.x * t.segs + q];
-          const __nv_bfloat16 o = f2bf(v);
-          if (MODE == 0) {
-            y[row] = o;
-          } else {
-            if (y) y[row] = o;
-            smp->best = argmax_better(smp->best, ArgMax{ds_score(*smp, bf2f(o), row), row});
-          }
-        }
+  const int steps = g.K >> 8;
+  float xr[kDsMaxSteps][8];
+  ds_load_x(xs, steps, lane, xr);
+  for (int s = (int)blockIdx.x; s < g.nj; s += (int)gridDim.x) {
+    const uint8_t* st = ds_acquire(ring, 0);
+    const float acc = ds_dot_seg(st + (size_t)warp * g.K * 2, steps, lane, xr);
+    ds_release(ring, 0, lane);
+    ring.taken += 1u;
+    const int row = s * 8 + warp;
+    if (lane == 0 && row < g.rows) {
+      const __nv_bfloat16 o = f2bf(acc);
+      if (!HEAD) {
+        y[row] = o;
+      } else {
+        if (y) y[row] = o;
+        smp->best = argmax_better(smp->best, ArgMax{ds_score(*smp, bf2f(o), row), row});
       }
     }
-    ring.consumed += 1u;
   }
+}
+// gate|up pairs: act[i] = bf16(silu(bf16 g_i) * bf16 u_i)   (layers/activation.py:11-14 on the bf16-rounded linear output)
+SSDK_DEVINL void ds_consume_pair(DsRing& ring, const DsGeom& g, const float* xs, __nv_bfloat16* act) {
+  if ((int)blockIdx.x >= g.nj) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int steps = g.K >> 8;
+  float xr[kDsMaxSteps][8];
+  ds_load_x(xs, steps, lane, xr);
+  for (int s = (int)blockIdx.x; s < g.nj; s += (int)gridDim.x) {
+    const uint8_t* sg = ds_acquire(ring, 0);
+    float gate = ds_dot_seg(sg + (size_t)warp * g.K * 2, steps, lane, xr);
+    ds_release(ring, 0, lane);
+    const uint8_t* su = ds_acquire(ring, 1);
+    float up = ds_dot_seg(su + (size_t)warp * g.K * 2, steps, lane, xr);
+    ds_release(ring, 1, lane);
+    ring.taken += 2u;
+    const int i = s * 8 + warp;
+    if (lane == 0 && i < g.rows) {
+      gate = bf16_round(gate);
+      up = bf16_round(up);
+      act[i] = f2bf((gate / (1.0f + __expf(-gate))) * up);
+    }
+  }
+}
+// rows of a K > 2048 matrix: the warps split (row, K segment) units; partial sums meet in shared memory, summed in
+// segment order
+SSDK_DEVINL void ds_consume_split(DsRing& ring, const DsGeom& g, const float* xs, float* res, __nv_bfloat16* y) {
+  if ((int)blockIdx.x >= g.nj) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_in_job = warp / g.segs, seg = warp - row_in_job * g.segs;
+  const int seg_len = g.K / g.segs, steps = seg_len >> 8;
+  float xr[kDsMaxSteps][8];
+  ds_load_x(xs + seg * seg_len, steps, lane, xr);
+  const size_t w_off = ((size_t)row_in_job * g.K + (size_t)seg * seg_len) * 2;
+  unsigned it = 0;
+  for (int s = (int)blockIdx.x; s < g.nj; s += (int)gridDim.x, ++it) {
+    const uint8_t* st = ds_acquire(ring, 0);
+    const float acc = ds_dot_seg(st + w_off, steps, lane, xr);
+    ds_release(ring, 0, lane);
+    ring.taken += 1u;
+    float* rb = res + (it & 1u) * kDsWarps;  // double buffered: the readers of job i may still be busy while job i+1 is summed
+    if (lane == 0) rb[warp] = acc;
+    ds_sync();
+    if ((int)threadIdx.x < g.rpj) {
+      const int row = s * g.rpj + (int)threadIdx.x;
+      if (row < g.rows) {
+        float v = 0.f;
+        for (int q = 0; q < g.segs; ++q) v += rb[(int)threadIdx.x * g.segs + q];
+        y[row] = f2bf(v);
+      }
+    }
+  }
+}
+SSDK_DEVINL void ds_consume(DsRing& ring, const DsGeom& g, const float* xs, float* res, __nv_bfloat16* y) {
+  if (g.kind == DS_PLAIN) ds_consume_plain<false>(ring, g, xs, y, nullptr);
+  else ds_consume_split(ring, g, xs, res, y);
+}
+
+SSDK_DEVINL float ds_block_sum(float v, float* red) {  // all consumer threads get the result
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  ds_sync();
+  if (lane == 0) red[wid] = v;
+  ds_sync();
+  float t = (lane < kDsWarps) ? red[lane] : 0.f;
+  return warp_sum(t);
 }
 
 // xs[i] = bf16r( r_i * rsqrt(mean r^2 + eps) * w_i ),  r = a (+ b) in fp32;  resid_out = bf16(r) (written by CTA 0 only).
@@ -321,7 +381,7 @@ SSDK_DEVINL void ds_consume(const DsParams& p, DsRing& ring, int l, int m, const
 SSDK_DEVINL void ds_norm_prologue(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* resid_out,
                                   const __nv_bfloat16* w, float eps, int d, float* xs, float* red) {
   float ss = 0.f;
-  for (int i = threadIdx.x * 8; i < d; i += kDsThreads * 8) {
+  for (int i = threadIdx.x * 8; i < d; i += kDsConsumers * 8) {
     float x[8];
     unpack_bf16x8(ds_ldcg16(a + i), x);
     if (b) {
@@ -337,15 +397,25 @@ SSDK_DEVINL void ds_norm_prologue(const __nv_bfloat16* a, const __nv_bfloat16* b
       ss += x[j] * x[j];
     }
   }
-  ss = block_sum(ss, red);
+  ss = ds_block_sum(ss, red);
   const float rstd = rsqrtf(ss / (float)d + eps);
-  for (int i = threadIdx.x * 8; i < d; i += kDsThreads * 8) {
+  for (int i = threadIdx.x * 8; i < d; i += kDsConsumers * 8) {
     float wv[8];
     unpack_bf16x8(*reinterpret_cast<const uint4*>(w + i), wv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) xs[i + j] = bf16_round(xs[i + j] * rstd * wv[j]);
   }
-  __syncthreads();
+  ds_sync();
+}
+// xs = fp32(v[0 .. n)) for an L2-resident bf16 vector
+SSDK_DEVINL void ds_load_vec(const __nv_bfloat16* v, int n, float* xs) {
+  for (int i = threadIdx.x * 8; i < n; i += kDsConsumers * 8) {
+    float x[8];
+    unpack_bf16x8(ds_ldcg16(v + i), x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xs[i + j] = x[j];
+  }
+  ds_sync();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,7 +424,7 @@ SSDK_DEVINL void ds_norm_prologue(const __nv_bfloat16* a, const __nv_bfloat16* b
 // token comes from shared memory, never from the cache) and writes (o, m, l) per query head.
 // ---------------------------------------------------------------------------------------------
 template <int HD, int GMAX>
-SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, int ctx, float* sm) {
+SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, int ctx, float* sm, int* flag) {
   constexpr int HALF = HD / 2;
   constexpr int EPL = HD / 32;  // elements per lane in the dot layout (dims lane*EPL ..)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -420,7 +490,7 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
       }
     }
   }
-  __syncthreads();
+  ds_sync();
 
   // ---- KV store of the new token (one unit per kv head) ----
   const int blk_new = p.block_table[pos / p.block_size];
@@ -428,7 +498,7 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
     const size_t slot = (size_t)blk_new * p.block_size + pos % p.block_size;
     __nv_bfloat16* kc = p.k_cache + (size_t)layer * p.cache_layer_stride + (slot * p.KV + h) * HD;
     __nv_bfloat16* vc = p.v_cache + (size_t)layer * p.cache_layer_stride + (slot * p.KV + h) * HD;
-    for (int i = threadIdx.x; i < HD; i += kDsThreads) {
+    for (int i = threadIdx.x; i < HD; i += kDsConsumers) {
       kc[i] = f2bf(sk[i]);
       vc[i] = f2bf(sv[i]);
     }
@@ -454,45 +524,60 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
   }
   const __nv_bfloat16* kbase = p.k_cache + (size_t)layer * p.cache_layer_stride;
   const __nv_bfloat16* vbase = p.v_cache + (size_t)layer * p.cache_layer_stride;
-  for (int t = t0 + warp; t < t1; t += kDsWarps) {
-    float kv[EPL], vv[EPL];
-    if (t == pos) {
+  // four tokens per warp iteration: all eight K / V loads are in flight before the first score is computed (one token
+  // per iteration exposed a full L2 / HBM round trip per token)
+  constexpr int TB = 4;
+  for (int tb = t0 + warp; tb < t1; tb += TB * kDsWarps) {
+    float kv[TB][EPL], vv[TB][EPL];
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        kv[e] = sk[lane * EPL + e];
-        vv[e] = sv[lane * EPL + e];
-      }
-    } else {
-      const int blk = p.block_table[t / p.block_size];
-      const size_t off = (((size_t)blk * p.block_size + t % p.block_size) * p.KV + h) * HD + lane * EPL;
-      if constexpr (EPL == 2) {
-        const float2 a = ds_bf2(__ldcg(reinterpret_cast<const uint32_t*>(kbase + off)));
-        const float2 b = ds_bf2(__ldcg(reinterpret_cast<const uint32_t*>(vbase + off)));
-        kv[0] = a.x; kv[1] = a.y; vv[0] = b.x; vv[1] = b.y;
+    for (int u = 0; u < TB; ++u) {
+      const int t = tb + u * kDsWarps;
+      if (t >= t1) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) kv[u][e] = vv[u][e] = 0.f;
+      } else if (t == pos) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          kv[u][e] = sk[lane * EPL + e];
+          vv[u][e] = sv[lane * EPL + e];
+        }
       } else {
-        static_assert(EPL == 2 || EPL == 4, "head_dim 64 or 128");
-        const uint2 a = __ldcg(reinterpret_cast<const uint2*>(kbase + off));
-        const uint2 b = __ldcg(reinterpret_cast<const uint2*>(vbase + off));
-        float2 f = ds_bf2(a.x); kv[0] = f.x; kv[1] = f.y;
-        f = ds_bf2(a.y); kv[EPL - 2] = f.x; kv[EPL - 1] = f.y;
-        f = ds_bf2(b.x); vv[0] = f.x; vv[1] = f.y;
-        f = ds_bf2(b.y); vv[EPL - 2] = f.x; vv[EPL - 1] = f.y;
+        const int blk = p.block_table[t / p.block_size];
+        const size_t off = (((size_t)blk * p.block_size + t % p.block_size) * p.KV + h) * HD + lane * EPL;
+        if constexpr (EPL == 2) {
+          const float2 a = ds_bf2(__ldcg(reinterpret_cast<const uint32_t*>(kbase + off)));
+          const float2 b = ds_bf2(__ldcg(reinterpret_cast<const uint32_t*>(vbase + off)));
+          kv[u][0] = a.x; kv[u][1] = a.y; vv[u][0] = b.x; vv[u][1] = b.y;
+        } else {
+          static_assert(EPL == 2 || EPL == 4, "head_dim 64 or 128");
+          const uint2 a = __ldcg(reinterpret_cast<const uint2*>(kbase + off));
+          const uint2 b = __ldcg(reinterpret_cast<const uint2*>(vbase + off));
+          float2 f = ds_bf2(a.x); kv[u][0] = f.x; kv[u][1] = f.y;
+          f = ds_bf2(a.y); kv[u][EPL - 2] = f.x; kv[u][EPL - 1] = f.y;
+          f = ds_bf2(b.x); vv[u][0] = f.x; vv[u][1] = f.y;
+          f = ds_bf2(b.y); vv[u][EPL - 2] = f.x; vv[u][EPL - 1] = f.y;
+        }
       }
     }
 #pragma unroll
-    for (int g = 0; g < GMAX; ++g) {
-      if (g < G) {
-        float sc = 0.f;
+    for (int u = 0; u < TB; ++u) {
+      if (tb + u * kDsWarps < t1) {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) sc = fmaf(qreg[g][e], kv[e], sc);
-        sc = warp_sum(sc) * p.scale_log2;
-        const float mn = fmaxf(m[g], sc);
-        const float corr = exp2f(m[g] - mn);  // m = -inf -> 0
-        const float pr = exp2f(sc - mn);
-        l[g] = l[g] * corr + pr;
+        for (int g = 0; g < GMAX; ++g) {
+          if (g < G) {
+            float sc = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[g][e] = acc[g][e] * corr + pr * vv[e];
-        m[g] = mn;
+            for (int e = 0; e < EPL; ++e) sc = fmaf(qreg[g][e], kv[u][e], sc);
+            sc = warp_sum(sc) * p.scale_log2;
+            const float mn = fmaxf(m[g], sc);
+            const float corr = exp2f(m[g] - mn);  // m = -inf -> 0
+            const float pr = exp2f(sc - mn);
+            l[g] = l[g] * corr + pr;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) acc[g][e] = acc[g][e] * corr + pr * vv[u][e];
+            m[g] = mn;
+          }
+        }
       }
     }
   }
@@ -510,8 +595,8 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
       }
     }
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < G * HD; idx += kDsThreads) {
+  ds_sync();
+  for (int idx = threadIdx.x; idx < G * HD; idx += kDsConsumers) {
     const int g = idx / HD, dim = idx - g * HD;
     float mx = -INFINITY;
     for (int w = 0; w < kDsWarps; ++w) mx = fmaxf(mx, sred[((size_t)w * G + g) * LDR + HD]);
@@ -531,80 +616,84 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
       out[HD + 1] = ll;
     }
   }
-  __syncthreads();
+  // ---- the LAST split of this kv head to finish merges the head group's partials into the attention output vector, so
+  //      that phase C only has to load 2 * H * HD bytes (every CTA merging every head cost ~7 us per layer) ----
+  ds_sync();  // the partials of every thread are ordered before thread 0's acq_rel ticket
+  if (threadIdx.x == 0) *flag = (atom_add_acq_rel_gpu(p.attn_ticket + h, 1u) == (unsigned)kDsSplits - 1u) ? 1 : 0;
+  ds_sync();
+  if (*flag) {
+    if (threadIdx.x == 0) st_relaxed_gpu_u32(p.attn_ticket + h, 0u);  // next use: a later phase B, device-wide barriers away
+    for (int idx = threadIdx.x; idx < G * HD; idx += kDsConsumers) {
+      const int g = idx / HD, dim = idx - g * HD;
+      const float* base = p.attn_part + (size_t)(h * G + g) * kDsSplits * LDR;
+      float ms[kDsSplits], ls[kDsSplits], os[kDsSplits];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < kDsSplits; ++q) {
+        ms[q] = __ldcg(base + q * LDR + HD);
+        ls[q] = __ldcg(base + q * LDR + HD + 1);
+        os[q] = __ldcg(base + q * LDR + dim);
+        mx = fmaxf(mx, ms[q]);
+      }
+      float o = 0.f, l = 0.f;
+#pragma unroll
+      for (int q = 0; q < kDsSplits; ++q) {
+        const float wt = (ms[q] == -INFINITY) ? 0.f : exp2f(ms[q] - mx);
+        o += os[q] * wt;
+        l += ls[q] * wt;
+      }
+      p.vec_attn[(size_t)(h * G + g) * HD + dim] = f2bf(l > 0.f ? o / l : 0.f);
+    }
+  }
+  ds_sync();
 }
 
-// phase C prologue: attention output of every head from the split partials -> xs (bf16-rounded), recomputed per CTA
-template <int HD>
-SSDK_DEVINL void ds_combine_prologue(const DsParams& p, float* xs) {
-  constexpr int LDR = HD + 2;
-  for (int idx = threadIdx.x; idx < p.H * HD; idx += kDsThreads) {
-    const int head = idx / HD, dim = idx - head * HD;
-    const float* base = p.attn_part + (size_t)head * kDsSplits * LDR;
-    float ms[kDsSplits], ls[kDsSplits], os[kDsSplits];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int s = 0; s < kDsSplits; ++s) {
-      ms[s] = __ldcg(base + s * LDR + HD);
-      ls[s] = __ldcg(base + s * LDR + HD + 1);
-      os[s] = __ldcg(base + s * LDR + dim);
-      mx = fmaxf(mx, ms[s]);
-    }
-    float o = 0.f, l = 0.f;
-#pragma unroll
-    for (int s = 0; s < kDsSplits; ++s) {
-      const float wt = (ms[s] == -INFINITY) ? 0.f : exp2f(ms[s] - mx);
-      o += os[s] * wt;
-      l += ls[s] * wt;
-    }
-    xs[idx] = bf16_round(l > 0.f ? o / l : 0.f);
-  }
-  __syncthreads();
-}
 
 template <int HD, int GMAX>
 __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __grid_constant__ DsParams p) {
   SSDK_DYN_SMEM(uint8_t, ds_smem);
-  SSDK_STATIC_SMEM(uint64_t, full_bar, kDsMaxStages);
+  SSDK_STATIC_SMEM(uint64_t, full_bar, kDsMaxSlots);
+  SSDK_STATIC_SMEM(uint64_t, empty_bar, kDsMaxSlots);
+  SSDK_STATIC_SMEM(DsGeom, geom, 5);
   SSDK_STATIC_SMEM(float, red, 32);
   SSDK_STATIC_SMEM(float, res, 2 * kDsWarps);
   SSDK_STATIC_SMEM(ArgMax, ared, 32);
   SSDK_SHARED_VAR(int, tok_s);
-  // dynamic shared memory: [ring: n_stages x 32 KB][xs: max(d, ffn, H*HD) floats][attention scratch]
-  DsRing ring;
-  ring.base = ds_smem;
-  ring.full = full_bar;
-  ring.n_stages = p.n_stages;
-  ring.consumed = 0u;
-  float* xs = reinterpret_cast<float*>(ds_smem + (size_t)p.n_stages * kDsStageBytes);
+  SSDK_SHARED_VAR(int, flag_s);
+  // dynamic shared memory: [ring: n_slots x 32 KB][xs: max(d, ffn, H*HD) floats][attention scratch]
+  float* xs = reinterpret_cast<float*>(ds_smem + (size_t)p.n_slots * kDsSlotBytes);
   float* scratch = xs + max(max(p.d, p.ffn), p.H * HD);
   if (threadIdx.x == 0) {
     trace_mark(TR_MISC);
-    for (int s = 0; s < p.n_stages; ++s) mbar_init(&full_bar[s], 1);
+    ds_geometry(p.d, (p.H + 2 * p.KV) * HD, false, &geom[DS_QKV]);
+    ds_geometry(p.H * HD, p.d, false, &geom[DS_O]);
+    ds_geometry(p.d, p.ffn, true, &geom[DS_GU]);
+    ds_geometry(p.ffn, p.d, false, &geom[DS_DOWN]);
+    ds_geometry(p.d, p.vocab, false, &geom[DS_HEAD]);
+    for (int s = 0; s < p.n_slots; ++s) {
+      mbar_init(&full_bar[s], 1);           // the producer's arrive.expect_tx + the copy's transaction bytes
+      mbar_init(&empty_bar[s], kDsWarps);   // one arrive per consumer warp
+    }
     fence_mbar_init();
-    // the weights do not depend on anything this launch computes: fill the ring and request the L2 window at once
-    ds_cursor_init<HD>(p, ring.issue);
-    for (int s = 0; s < p.n_stages && ring.issue.valid; ++s) {
-      const DsJob j = ds_job<HD>(p, ring.issue);
-      uint8_t* dst = ring.base + (size_t)s * kDsStageBytes;
-      mbar_arrive_expect_tx(&ring.full[s], j.bytes0 + j.bytes1);
-      bulk_load_g2s(dst, j.src0, j.bytes0, &ring.full[s]);
-      if (j.bytes1) bulk_load_g2s(dst + j.off1, j.src1, j.bytes1, &ring.full[s]);
-      ds_cursor_advance<HD>(p, ring.issue);
-    }
-    ring.ahead = ring.issue;  // from here on `ahead` stays l2_ahead jobs in front of `issue` (ds_issue moves both)
-    for (int s = 0; s < p.l2_ahead && ring.ahead.valid; ++s) {
-      const DsJob a = ds_job<HD>(p, ring.ahead);
-      bulk_prefetch_l2(a.src0, a.bytes0);
-      if (a.bytes1) bulk_prefetch_l2(a.src1, a.bytes1);
-      ds_cursor_advance<HD>(p, ring.ahead);
-    }
   }
-  __syncthreads();  // mbarriers initialised before anybody waits on them
+  __syncthreads();  // the only block-wide barrier: mbarriers and the geometry table exist before anybody uses them
 
+  if (threadIdx.x >= kDsConsumers) {
+    // ===================== producer warp: the weight stream never waits for a phase =====================
+    if (threadIdx.x == kDsConsumers) ds_producer(p, geom, ds_smem, full_bar, empty_bar);
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  DsRing ring;
+  ring.base = ds_smem;
+  ring.full = full_bar;
+  ring.empty = empty_bar;
+  ring.n_slots = (unsigned)p.n_slots;
+  ring.taken = 0u;
   DsGridBar bar;
-  bar.state = p.bar_state;
-  bar.gen = 0;
+  bar.counter = reinterpret_cast<unsigned long long*>(p.bar_state);
+  bar.target = 0;
   bar.init();
 
   const int ctx_base = p.ctx0[0];
@@ -629,31 +718,41 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
         ds_norm_prologue(p.vec_down, resid[cur], resid[cur ^ 1], lw.in_norm, p.eps, p.d, xs, red);
       }
       cur ^= 1;
-      ds_consume<HD, 0>(p, ring, l, DS_QKV, xs, res, p.vec_qkv, nullptr);
+      ds_mark(f, 0);
+      ds_consume(ring, geom[DS_QKV], xs, res, p.vec_qkv);
+      ds_mark(f, 1);
       bar.sync();
-      // ---- B: RoPE + KV store + attention units ----
+      ds_mark(f, 2);
+#ifdef SSDK_TRACE_FINE
+      bar.sync();  // probe: a second barrier right after the first has no arrival skew -> its duration is the pure latency
+      ds_mark(f, 12);
+#endif
+      // ---- B: RoPE + KV store + attention units (+ merge by the last split of each kv head) ----
       for (int u = blockIdx.x; u < p.KV * kDsSplits; u += gridDim.x)
-        ds_attention_unit<HD, GMAX>(p, l, u / kDsSplits, u % kDsSplits, ctx, scratch);
+        ds_attention_unit<HD, GMAX>(p, l, u / kDsSplits, u % kDsSplits, ctx, scratch, &flag_s);
+      ds_mark(f, 3);
       bar.sync();
-      // ---- C: merge splits -> o-proj ----
-      ds_combine_prologue<HD>(p, xs);
-      ds_consume<HD, 0>(p, ring, l, DS_O, xs, res, p.vec_o, nullptr);
+      ds_mark(f, 4);
+      // ---- C: o-proj ----
+      ds_load_vec(p.vec_attn, p.H * HD, xs);
+      ds_consume(ring, geom[DS_O], xs, res, p.vec_o);
+      ds_mark(f, 5);
       bar.sync();
+      ds_mark(f, 6);
       // ---- D: add + post-attention norm -> gate|up with SiLU*mul ----
       ds_norm_prologue(p.vec_o, resid[cur], resid[cur ^ 1], lw.post_norm, p.eps, p.d, xs, red);
       cur ^= 1;
-      ds_consume<HD, 1>(p, ring, l, DS_GU, xs, res, p.vec_act, nullptr);
+      ds_mark(f, 7);
+      ds_consume_pair(ring, geom[DS_GU], xs, p.vec_act);
+      ds_mark(f, 8);
       bar.sync();
+      ds_mark(f, 9);
       // ---- E: down-proj ----
-      for (int i = threadIdx.x * 8; i < p.ffn; i += kDsThreads * 8) {
-        float x[8];
-        unpack_bf16x8(ds_ldcg16(p.vec_act + i), x);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xs[i + j] = x[j];
-      }
-      __syncthreads();
-      ds_consume<HD, 0>(p, ring, l, DS_DOWN, xs, res, p.vec_down, nullptr);
+      ds_load_vec(p.vec_act, p.ffn, xs);
+      ds_consume(ring, geom[DS_DOWN], xs, res, p.vec_down);
+      ds_mark(f, 10);
       bar.sync();
+      ds_mark(f, 11);
     }
     if (!ds_has_head(p, f)) break;
     // ---- final add + norm (models/llama3.py:198) -> lm_head; logits rounded to bf16 like every linear output ----
@@ -664,24 +763,34 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
     smp.seed = seed;
     smp.call_id = call0 + (uint64_t)f;
     smp.best = ArgMax{-INFINITY, 0x7fffffff};
-    ds_consume<HD, 2>(p, ring, p.L, DS_HEAD, xs, res, p.logits ? p.logits + (size_t)f * p.logits_ld : nullptr, &smp);
-    // ---- sampling: per-CTA best -> device-wide reduction (every CTA learns the token) ----
-    if (threadIdx.x < 32) {
-      const ArgMax b = warp_argmax(smp.best);  // threads 0 .. R-1 hold candidates, the others the neutral element
-      if (threadIdx.x == 0) p.samp_partial[blockIdx.x] = b;
+    ds_consume_plain<true>(ring, geom[DS_HEAD], xs, p.logits ? p.logits + (size_t)f * p.logits_ld : nullptr, &smp);
+    // ---- sampling: per-warp best -> per-CTA best -> device-wide reduction (every CTA learns the token) ----
+    if ((threadIdx.x & 31) == 0) ared[threadIdx.x >> 5] = smp.best;
+    ds_sync();
+    if (threadIdx.x == 0) {
+      ArgMax b = ared[0];
+      for (int w = 1; w < kDsWarps; ++w) b = argmax_better(b, ared[w]);
+      p.samp_partial[blockIdx.x] = b;
     }
     bar.sync();
     {
       ArgMax a{-INFINITY, 0x7fffffff};
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += kDsThreads) {
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += kDsConsumers) {
         ArgMax q;
         q.v = __ldcg(&p.samp_partial[i].v);
         q.i = __ldcg(&p.samp_partial[i].i);
         a = argmax_better(a, q);
       }
-      a = block_argmax(a, ared);
-      if (threadIdx.x == 0) tok_s = a.i;
-      __syncthreads();
+      a = warp_argmax(a);
+      ds_sync();  // ared was read above by thread 0 of THIS CTA only before the device-wide barrier: safe to reuse
+      if ((threadIdx.x & 31) == 0) ared[threadIdx.x >> 5] = a;
+      ds_sync();
+      if (threadIdx.x == 0) {
+        ArgMax b = ared[0];
+        for (int w = 1; w < kDsWarps; ++w) b = argmax_better(b, ared[w]);
+        tok_s = b.i;
+      }
+      ds_sync();
       tok = tok_s;
       if (blockIdx.x == 0 && threadIdx.x == 0) p.tok_buf[f + 1] = tok;
     }

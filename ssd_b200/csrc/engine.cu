@@ -403,9 +403,9 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.ver_rows = (RowPart*)take((size_t)kVerifyMaxRows * kVerifyCtas * sizeof(RowPart));
   w.ver_rec = (RecPart*)take((size_t)16 * kVerifyCtas * sizeof(RecPart));
   w.ver_counters = (unsigned*)take(64);
-  w.ds_vec = (bf16*)take((size_t)(qmax + 4 * dmax + fmax + 64) * 2);
+  w.ds_vec = (bf16*)take((size_t)(qmax + 4 * dmax + fmax + Hmax * hdmax + 64) * 2);
   w.ds_attn = (float*)take((size_t)Hmax * kDsSplits * (hdmax + 2) * 4);
-  w.ds_sync = (unsigned*)take(64);
+  w.ds_sync = (unsigned*)take(256);
   return (int64_t)align_up(off, 1024);
 }
 
@@ -830,7 +830,7 @@ __global__ void advance_kernel(int32_t* __restrict__ ctx, int64_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
 // streaming draft kernel: the K+1 draft forwards + K samplings of a step in ONE cooperative launch (draft_stream.cuh)
-// SSDK_DRAFT_STREAM=0 keeps the kernel-per-op path; SSDK_DRAFT_L2_AHEAD=n requests n further stages per CTA into L2.
+// SSDK_DRAFT_STREAM=0 keeps the kernel-per-op path.
 // ------------------------------------------------------------------------------------------
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
@@ -848,21 +848,19 @@ static size_t ds_fixed_smem(const Model& m) {
   const size_t scratch = (size_t)gmax * m.hd + 2 * m.hd + (size_t)kDsWarps * gmax * (m.hd + 2);
   return (xs + scratch) * 4 + 256;
 }
-static int ds_ring_stages(const Model& m) {
+static int ds_ring_slots(const Model& m) {
   const size_t fixed = ds_fixed_smem(m);
-  if (fixed + 3 * (size_t)kDsStageBytes > (size_t)kMaxDynSmem) return 0;
-  return (int)std::min<size_t>(kDsMaxStages, ((size_t)kMaxDynSmem - fixed) / kDsStageBytes);
-}
-static bool ds_k_ok(int K) {
-  if (K < 256 || K > 8192) return false;
-  int R, segs;
-  ds_geometry(K, &R, &segs);
-  return K % (256 * segs) == 0;
+  if (fixed + 3 * (size_t)kDsSlotBytes > (size_t)kMaxDynSmem) return 0;
+  return (int)std::min<size_t>(kDsMaxSlots, ((size_t)kMaxDynSmem - fixed) / kDsSlotBytes);
 }
 static bool draft_stream_supported(const Model& m, int B) {
   const int G = m.KV ? m.H / m.KV : 0;
+  DsGeom g;
   return B == 1 && m.cfg.tp_size == 1 && m.cfg.layers <= kDsMaxLayers && (m.hd == 64 || m.hd == 128) && G >= 1 && G <= 8 &&
-         m.H % m.KV == 0 && ds_k_ok(m.d) && ds_k_ok(m.H * m.hd) && ds_k_ok(m.ffn) && m.d % 8 == 0 && ds_ring_stages(m) >= 3;
+         m.H % m.KV == 0 && m.KV <= 32 && m.d % 8 == 0 && (m.H * m.hd) % 8 == 0 && m.ffn % 8 == 0 &&
+         ds_geometry(m.d, m.qkv_dim, false, &g) && ds_geometry(m.H * m.hd, m.d, false, &g) &&
+         ds_geometry(m.d, m.ffn, true, &g) && ds_geometry(m.ffn, m.d, false, &g) && ds_geometry(m.d, m.cfg.vocab, false, &g) &&
+         ds_ring_slots(m) >= 3;
 }
 template <int HD, int GMAX>
 static int launch_draft_stream(Launcher& L, const DsParams& p, size_t smem) {
@@ -906,6 +904,7 @@ static int enqueue_draft_stream(ssdk_engine* e, Launcher& L, int64_t* tok_buf, i
   p.ctx0 = ctx0; p.block_table = block_table;
   bf16* v = w.ds_vec;
   p.vec_qkv = v; v += align_up((size_t)m.qkv_dim, 8);
+  p.vec_attn = v; v += (size_t)m.H * m.hd;
   p.vec_o = v; v += m.d;
   p.vec_down = v; v += m.d;
   p.resid0 = v; v += m.d;
@@ -916,14 +915,14 @@ static int enqueue_draft_stream(ssdk_engine* e, Launcher& L, int64_t* tok_buf, i
   p.temp = temp; p.dyn = dyn;
   p.samp_partial = w.samp_partial;
   p.bar_state = w.ds_sync;
-  p.n_stages = ds_ring_stages(m);
-  p.l2_ahead = std::max(0, env_int("SSDK_DRAFT_L2_AHEAD", 0));
+  p.attn_ticket = w.ds_sync + 8;
+  p.n_slots = ds_ring_slots(m);
   for (int l = 0; l < p.L; ++l) {
     const LayerW& lw = m.layers[l];
     p.layers[l] = DsLayer{lw.qkv.ptr, lw.o.ptr, lw.gate_up.ptr, lw.down.ptr, lw.input_norm, lw.post_norm, lw.q_norm, lw.k_norm};
   }
   const int G = m.H / m.KV, gmax = G <= 4 ? 4 : 8;
-  const size_t smem = ds_fixed_smem(m) + (size_t)p.n_stages * kDsStageBytes;
+  const size_t smem = ds_fixed_smem(m) + (size_t)p.n_slots * kDsSlotBytes;
   if (m.hd == 64 && gmax == 4) return launch_draft_stream<64, 4>(L, p, smem);
   if (m.hd == 64 && gmax == 8) return launch_draft_stream<64, 8>(L, p, smem);
   if (m.hd == 128 && gmax == 4) return launch_draft_stream<128, 4>(L, p, smem);

@@ -80,6 +80,7 @@ struct Cta {
   std::vector<std::unique_ptr<Warp>> warps;
   std::mutex mu;
   std::map<int, std::vector<unsigned char>> statics;
+  std::map<int, std::unique_ptr<std::barrier<>>> named;  // bar.sync id, count
 };
 struct ThreadCtx {
   Cta* cta = nullptr;
@@ -101,6 +102,21 @@ T* static_smem(size_t n, int key) {
 inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 inline void __syncthreads() { emu::tctx.cta->bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::tctx.cta->warps[threadIdx.x >> 5]->bar.arrive_and_wait(); }
+namespace emu {
+// bar.sync id, count: a barrier among `count` threads of the CTA (the same `count` every time for a given id)
+inline void named_barrier(int id, int count) {
+  Cta* c = tctx.cta;
+  std::barrier<>* b;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    auto& slot = c->named[id];
+    if (!slot) slot = std::make_unique<std::barrier<>>(count);
+    b = slot.get();
+  }
+  b->arrive_and_wait();
+}
+}  // namespace emu
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __trap() {
   std::fprintf(stderr, "[cuda_emu] __trap()\n");

@@ -63,12 +63,12 @@ int main(int argc, char** argv) {
   const size_t cache_layer = (size_t)nslots * KV * hd;
   auto kc = r.vec<bf16>(cache_layer * L), vc = r.vec<bf16>(cache_layer * L);
 
-  std::vector<bf16> vecs((size_t)qkv_dim + 4 * d + ffn + 64), logits((size_t)n_fwd * vocab);
+  std::vector<bf16> vecs((size_t)qkv_dim + 4 * d + ffn + H * hd + 64), logits((size_t)n_fwd * vocab);
   std::vector<float> attn((size_t)H * ssdk::kDsSplits * (hd + 2));
   std::vector<ssdk::ArgMax> partial(grid);
   std::vector<int64_t> tok_buf(n_fwd + 1, -1);
   tok_buf[0] = tokens[0];
-  unsigned sync[2] = {0, 0};
+  alignas(8) unsigned sync[64] = {0};
   int32_t ctx0_dev = ctx0;
 
   ssdk::DsParams p;
@@ -84,6 +84,7 @@ int main(int argc, char** argv) {
   p.ctx0 = &ctx0_dev; p.block_table = block_table.data();
   bf16* v = vecs.data();
   p.vec_qkv = v; v += (qkv_dim + 7) / 8 * 8;
+  p.vec_attn = v; v += H * hd;
   p.vec_o = v; v += d;
   p.vec_down = v; v += d;
   p.resid0 = v; v += d;
@@ -94,14 +95,15 @@ int main(int argc, char** argv) {
   p.temp = &temp; p.dyn = nullptr; p.seed = rng[0]; p.call_base = rng[1];
   p.samp_partial = partial.data();
   p.bar_state = sync;
-  p.n_stages = n_stages; p.l2_ahead = 2;
+  p.attn_ticket = sync + 8;
+  p.n_slots = n_stages;
   for (int l = 0; l < L; ++l)
     p.layers[l] = ssdk::DsLayer{lw[l].qkv.data(), lw[l].o.data(), lw[l].gate_up.data(), lw[l].down.data(),
                                 lw[l].in_norm.data(), lw[l].post_norm.data(), lw[l].q_norm.data(), lw[l].k_norm.data()};
   const int G = H / KV, gmax = G <= 4 ? 4 : 8;
   const size_t xs = (size_t)std::max(std::max(d, ffn), H * hd);
   const size_t scratch = (size_t)gmax * hd + 2 * hd + (size_t)ssdk::kDsWarps * gmax * (hd + 2);
-  const size_t smem = (xs + scratch) * 4 + 256 + (size_t)n_stages * ssdk::kDsStageBytes;
+  const size_t smem = (xs + scratch) * 4 + 256 + (size_t)n_stages * ssdk::kDsSlotBytes;
   // two launches on the same barrier state: the generation-based barrier must carry over
   for (int rep = 0; rep < 2; ++rep) {
     if (rep == 1) {  // second launch: same inputs again (KV rows are simply rewritten with the same values)
@@ -111,8 +113,15 @@ int main(int argc, char** argv) {
     else if (hd == 64) emu::launch(ssdk::draft_stream_kernel<64, 8>, p, grid, ssdk::kDsThreads, smem);
     else if (gmax == 4) emu::launch(ssdk::draft_stream_kernel<128, 4>, p, grid, ssdk::kDsThreads, smem);
     else emu::launch(ssdk::draft_stream_kernel<128, 8>, p, grid, ssdk::kDsThreads, smem);
-    if (sync[0] != 0) {
-      std::cerr << "barrier arrival count not back to zero\n";
+    for (int i = 2; i < 64; ++i)
+      if (sync[i] != 0) {
+        std::cerr << "attention ticket " << i << " not back to zero\n";
+        return 3;
+      }
+    unsigned long long arrivals;
+    std::memcpy(&arrivals, sync, 8);
+    if (arrivals % (unsigned long long)grid != 0) {
+      std::cerr << "barrier arrival counter is not a whole number of barriers\n";
       return 3;
     }
   }

@@ -17,7 +17,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _rank_main(rank, world, port, use_graph, use_symm, q):
+DIMS = {
+    # hidden, heads, kv_heads, ffn, vocab
+    "small": (256, 4, 2, 512, 1024),
+    # wide enough for the in-kernel split-K paths: o-proj K = 512 / rank (2 splits), down-proj K = 2048 / rank (8 splits,
+    # ticket reduction + publish from the last CTA of a tile), gate|up 64 tiles / rank (split-K SiLU epilogue)
+    "wide": (1024, 16, 2, 8192, 2048),
+}
+
+
+def _rank_main(rank, world, port, use_graph, use_symm, q, dims="small"):
     import torch.distributed as dist
     from oracle.model import ModelCfg, OracleModel, random_weights
     from oracle.spec import SpecSession, check_greedy_step, contiguous_block_tables
@@ -31,7 +40,8 @@ def _rank_main(rank, world, port, use_graph, use_symm, q):
                                 device_id=torch.device("cuda", rank))
         comm = create_nccl_comm(world, rank)
         K, B, bs, mb = 4, 2, 64, 3
-        tc = ModelCfg(hidden=256, layers=2, heads=4, kv_heads=2, head_dim=64, ffn=512, vocab=1024, max_pos=256)
+        hidden, heads, kvh, ffn, vocab = DIMS[dims]
+        tc = ModelCfg(hidden=hidden, layers=2, heads=heads, kv_heads=kvh, head_dim=64, ffn=ffn, vocab=vocab, max_pos=256)
         dc = ModelCfg(**{**tc.__dict__, "layers": 1})
         wt = random_weights(tc, 41)
         wd = {"embed": wt["embed"], "lm_head": wt["lm_head"], "final_norm": wt["final_norm"], "layers": [wt["layers"][0]]}
@@ -83,15 +93,16 @@ def _rank_main(rank, world, port, use_graph, use_symm, q):
         q.put((rank, "fail", traceback.format_exc(), None))
 
 
-@pytest.mark.parametrize("use_graph,use_symm", [(False, False), (True, False), (False, True), (True, True)])
-def test_tp2_spec_steps(use_graph, use_symm):
+@pytest.mark.parametrize("use_graph,use_symm,dims", [(False, False, "small"), (True, False, "small"), (False, True, "small"),
+                                                     (True, True, "small"), (True, True, "wide"), (False, True, "wide")])
+def test_tp2_spec_steps(use_graph, use_symm, dims):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, use_graph, use_symm, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, use_graph, use_symm, q, dims)) for r in range(2)]
     for p in procs:
         p.start()
     res = {}

@@ -67,9 +67,7 @@ def main():
 
     res = {}
     tmp = tempfile.mkdtemp()
-    modes = (("regular", {"SSDK_DRAFT_STREAM": "0"}), ("stream", {"SSDK_DRAFT_STREAM": "1"}),
-             ("stream_l2_4", {"SSDK_DRAFT_STREAM": "1", "SSDK_DRAFT_L2_AHEAD": "4"}),
-             ("stream_l2_16", {"SSDK_DRAFT_STREAM": "1", "SSDK_DRAFT_L2_AHEAD": "16"}))
+    modes = (("regular", {"SSDK_DRAFT_STREAM": "0"}), ("stream", {"SSDK_DRAFT_STREAM": "1"}))
     extra = ["--temp", str(TEMP)] if TEMP else []
     for mode, env in modes:
         out = os.path.join(tmp, mode + ".npz")

@@ -85,5 +85,24 @@ def phases(lo, hi, label):
         print(f"  {kind:8s} " + "  ".join(f"{k}={v[1] / v[0]:.2f}" for k, v in d.items()))
 
 
-phases(preps[0], preps[1], "first draft forward")
-phases(preps[-1], nk, "target verify forward")
+# streaming draft kernel: phase points of its second forward (ids 64 + point, draft_stream.cuh: ds_mark)
+pts = sorted((all_ts[i], all_ids[i] - 64) for i in range(n) if all_ids[i] >= 64)
+if pts:
+    label = {0: "A prologue done", 1: "A gemv done", 2: "A barrier", 3: "B attention done", 4: "B barrier", 5: "C gemv done",
+             6: "C barrier", 7: "D prologue done", 8: "D gemv done", 9: "D barrier", 10: "E gemv done", 11: "E barrier",
+             12: "probe barrier"}
+    gaps = collections.defaultdict(lambda: [0, 0.0])
+    for (t0, a), (t1, b) in zip(pts, pts[1:]):
+        g = gaps[(a, b)]
+        g[0] += 1
+        g[1] += (t1 - t0) / 1e3
+    print("--- draft_stream_kernel, second forward of the launch, mean gap (us) between phase points over the layers")
+    tot = 0.0
+    for (a, b), (c, us) in sorted(gaps.items()):
+        print(f"  {label.get(a, a):>18s} -> {label.get(b, b):<18s} n={c:3d} {us / c:7.2f}")
+        tot += us / c
+    print(f"  per layer {tot:.1f} us; forward span {(pts[-1][0] - pts[0][0]) / 1e3:.1f} us")
+if len(preps) >= 2:
+    phases(preps[0], preps[1], "first draft forward")
+if preps:
+    phases(preps[-1], nk, "target verify forward")
