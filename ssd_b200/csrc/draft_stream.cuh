@@ -77,6 +77,7 @@ struct DsParams {
   unsigned* bar_state;           // one 64-bit arrival counter (8-byte aligned), only ever grows; zero before the first launch
   unsigned* attn_ticket;         // [KV] arrival tickets of the split-KV units, zero between phases
   int n_slots;                   // ring depth (3 .. kDsMaxSlots)
+  int l2_ahead;                  // jobs requested into L2 beyond the ones in flight to shared memory (0 = off)
   DsLayer layers[kDsMaxLayers];
 };
 
@@ -187,11 +188,31 @@ SSDK_DEVINL void ds_cursor_settle(const DsParams& p, const DsGeom* geom, DsCurso
   }
 }
 
-// the producer: one lane walks the job sequence of this CTA and refills slots as the consumers release them
+// the producer: one lane walks the job sequence of this CTA and refills slots as the consumers release them.  Optionally
+// a second cursor runs l2_ahead jobs in front and only pulls those bytes into L2 (fire-and-forget): when the consumers sit
+// in a phase without weights (attention) or at a barrier, the ring is full and HBM would idle; the L2 window keeps it busy
+// and the later copies into shared memory hit L2.
+SSDK_DEVINL void ds_cursor_next(const DsParams& p, const DsGeom* geom, DsCursor& c) {
+  c.s += (int)gridDim.x;
+  if (c.s >= geom[c.m].nj) ds_cursor_settle(p, geom, c);
+}
+SSDK_DEVINL void ds_prefetch_job(const DsParams& p, const DsGeom* geom, const DsCursor& c) {
+  const DsGeom g = geom[c.m];
+  const __nv_bfloat16* w = ds_weight(p, c.l, c.m);
+  const int rows = min(g.rpj, g.rows - c.s * g.rpj);
+  const unsigned bytes = (unsigned)rows * (unsigned)g.K * 2u;
+  bulk_prefetch_l2(w + (size_t)c.s * g.rpj * g.K, bytes);
+  if (g.kind == DS_PAIR) bulk_prefetch_l2(w + ((size_t)g.rows + (size_t)c.s * g.rpj) * g.K, bytes);
+}
 SSDK_DEVINL void ds_producer(const DsParams& p, const DsGeom* geom, uint8_t* ring, uint64_t* full, uint64_t* empty) {
   DsCursor c;
   c.f = 0; c.l = 0; c.m = DS_QKV; c.s = (int)blockIdx.x; c.valid = p.n_fwd > 0;
   ds_cursor_settle(p, geom, c);
+  DsCursor a = c;  // L2 window: stays l2_ahead jobs in front of c
+  for (int i = 0; i < p.l2_ahead && a.valid; ++i) {
+    if (i >= 3) ds_prefetch_job(p, geom, a);  // the first jobs go to shared memory right away
+    ds_cursor_next(p, geom, a);
+  }
   unsigned n = 0;  // slots requested so far
   const unsigned S = (unsigned)p.n_slots;
   while (c.valid) {
@@ -208,8 +229,11 @@ SSDK_DEVINL void ds_producer(const DsParams& p, const DsGeom* geom, uint8_t* rin
       bulk_load_g2s(ring + (size_t)slot * kDsSlotBytes, src, bytes, &full[slot]);
       ++n;
     }
-    c.s += (int)gridDim.x;
-    if (c.s >= g.nj) ds_cursor_settle(p, geom, c);
+    ds_cursor_next(p, geom, c);
+    if (p.l2_ahead > 0 && a.valid) {
+      ds_prefetch_job(p, geom, a);
+      ds_cursor_next(p, geom, a);
+    }
   }
 }
 
@@ -423,8 +447,11 @@ SSDK_DEVINL void ds_load_vec(const __nv_bfloat16* v, int n, float* xs) {
 // q|k|v vector, stores k / v into the page slot (split 0 only), runs the online-softmax over its token range (the new
 // token comes from shared memory, never from the cache) and writes (o, m, l) per query head.
 // ---------------------------------------------------------------------------------------------
+SSDK_DEVINL int ds_num_splits(int ctx) {  // one split per 256 tokens of context: short contexts need no partials, no ticket, no merge
+  return min(kDsSplits, max(1, (ctx + 255) >> 8));
+}
 template <int HD, int GMAX>
-SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, int ctx, float* sm, int* flag) {
+SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, int ns, int ctx, float* sm, int* flag) {
   constexpr int HALF = HD / 2;
   constexpr int EPL = HD / 32;  // elements per lane in the dot layout (dims lane*EPL ..)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -505,7 +532,7 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
   }
 
   // ---- token range of this split ----
-  const int per = (ctx + kDsSplits - 1) / kDsSplits;
+  const int per = (ctx + ns - 1) / ns;
   const int t0 = s * per, t1 = min(ctx, t0 + per);
 
   // dot layout: lane owns dims [lane * EPL, lane * EPL + EPL)
@@ -609,17 +636,25 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
         ll += r[HD + 1] * wt;
       }
     }
-    float* out = p.attn_part + ((size_t)(h * G + g) * kDsSplits + s) * LDR;
-    out[dim] = o;  // un-normalised: sum_t 2^(s_t - mx) v_t
-    if (dim == 0) {
-      out[HD] = mx;
-      out[HD + 1] = ll;
+    if (ns == 1) {  // the only split: this is the attention output
+      p.vec_attn[(size_t)(h * G + g) * HD + dim] = f2bf(ll > 0.f ? o / ll : 0.f);
+    } else {
+      float* out = p.attn_part + ((size_t)(h * G + g) * kDsSplits + s) * LDR;
+      out[dim] = o;  // un-normalised: sum_t 2^(s_t - mx) v_t
+      if (dim == 0) {
+        out[HD] = mx;
+        out[HD + 1] = ll;
+      }
     }
+  }
+  if (ns == 1) {
+    ds_sync();  // scratch is reused by the next unit of this CTA
+    return;
   }
   // ---- the LAST split of this kv head to finish merges the head group's partials into the attention output vector, so
   //      that phase C only has to load 2 * H * HD bytes (every CTA merging every head cost ~7 us per layer) ----
   ds_sync();  // the partials of every thread are ordered before thread 0's acq_rel ticket
-  if (threadIdx.x == 0) *flag = (atom_add_acq_rel_gpu(p.attn_ticket + h, 1u) == (unsigned)kDsSplits - 1u) ? 1 : 0;
+  if (threadIdx.x == 0) *flag = (atom_add_acq_rel_gpu(p.attn_ticket + h, 1u) == (unsigned)ns - 1u) ? 1 : 0;
   ds_sync();
   if (*flag) {
     if (threadIdx.x == 0) st_relaxed_gpu_u32(p.attn_ticket + h, 0u);  // next use: a later phase B, device-wide barriers away
@@ -630,9 +665,10 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
       float mx = -INFINITY;
 #pragma unroll
       for (int q = 0; q < kDsSplits; ++q) {
-        ms[q] = __ldcg(base + q * LDR + HD);
-        ls[q] = __ldcg(base + q * LDR + HD + 1);
-        os[q] = __ldcg(base + q * LDR + dim);
+        const bool on = q < ns;
+        ms[q] = on ? __ldcg(base + q * LDR + HD) : -INFINITY;
+        ls[q] = on ? __ldcg(base + q * LDR + HD + 1) : 0.f;
+        os[q] = on ? __ldcg(base + q * LDR + dim) : 0.f;
         mx = fmaxf(mx, ms[q]);
       }
       float o = 0.f, l = 0.f;
@@ -728,8 +764,9 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
       ds_mark(f, 12);
 #endif
       // ---- B: RoPE + KV store + attention units (+ merge by the last split of each kv head) ----
-      for (int u = blockIdx.x; u < p.KV * kDsSplits; u += gridDim.x)
-        ds_attention_unit<HD, GMAX>(p, l, u / kDsSplits, u % kDsSplits, ctx, scratch, &flag_s);
+      const int ns = ds_num_splits(ctx);
+      for (int u = blockIdx.x; u < p.KV * ns; u += gridDim.x)
+        ds_attention_unit<HD, GMAX>(p, l, u / ns, u % ns, ns, ctx, scratch, &flag_s);
       ds_mark(f, 3);
       bar.sync();
       ds_mark(f, 4);

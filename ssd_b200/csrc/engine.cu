@@ -574,11 +574,16 @@ static PublishParams publish_params(ssdk_engine* e, int call_idx) {
   pb.rank = m.cfg.tp_rank;
   return pb;
 }
+// SSDK_FUSED_PUBLISH=1: the row-parallel GEMM publishes from its own epilogue (EPI_PUBLISH).  Off by default: measured on
+// B200 with Llama-3.1-70B it is slower than GEMM -> ar_publish_kernel at TP=2 (18.79 vs 18.23 ms/step) and TP=4 (14.44 vs
+// 13.97): the ticket + reduce + 8-byte remote stores of the last split-K CTA of a tile lengthen the GEMM's tail by more
+// than the kernel boundary they save, because the publish kernel spreads the same work over 28 CTAs x 256 threads with
+// 16-byte stores (profiles/r02_tp_fused_publish_ab.md).
 static bool fused_publish_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("SSDK_FUSED_PUBLISH");
-    v = (s && *s) ? (atoi(s) != 0 ? 1 : 0) : 1;
+    v = (s && *s) ? (atoi(s) != 0 ? 1 : 0) : 0;
   }
   return v == 1;
 }
@@ -830,7 +835,7 @@ __global__ void advance_kernel(int32_t* __restrict__ ctx, int64_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
 // streaming draft kernel: the K+1 draft forwards + K samplings of a step in ONE cooperative launch (draft_stream.cuh)
-// SSDK_DRAFT_STREAM=0 keeps the kernel-per-op path.
+// SSDK_DRAFT_STREAM=0 keeps the kernel-per-op path; SSDK_DRAFT_L2_AHEAD=n: L2 window of n jobs per CTA beyond the ring.
 // ------------------------------------------------------------------------------------------
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
@@ -917,6 +922,7 @@ static int enqueue_draft_stream(ssdk_engine* e, Launcher& L, int64_t* tok_buf, i
   p.bar_state = w.ds_sync;
   p.attn_ticket = w.ds_sync + 8;
   p.n_slots = ds_ring_slots(m);
+  p.l2_ahead = std::max(0, env_int("SSDK_DRAFT_L2_AHEAD", 0));
   for (int l = 0; l < p.L; ++l) {
     const LayerW& lw = m.layers[l];
     p.layers[l] = DsLayer{lw.qkv.ptr, lw.o.ptr, lw.gate_up.ptr, lw.down.ptr, lw.input_norm, lw.post_norm, lw.q_norm, lw.k_norm};

@@ -79,13 +79,13 @@ SSDK_DEVINL bool splitk_ticket_reduce(uint32_t* r, const GemmParams& p, int col,
     for (int m = 0; m < UMMA_N; ++m)
       if (m < p.M) out[(size_t)m * p.sk_width + col] = __uint_as_float(r[m]);
   }
-  __threadfence();
+  // the partial stores of the 128 epilogue threads are ordered before thread 64's acq_rel ticket by the named barrier
+  // (one MEMBAR on one thread instead of a __threadfence on all of them); the same atomic is the acquire for the last CTA
   asm volatile("bar.sync 1, 128;" ::: "memory");
-  if (threadIdx.x == 64) *smem_flag = (atomicAdd(&p.sk_counters[tile], 1u) == (unsigned)S - 1u) ? 1 : 0;
+  if (threadIdx.x == 64) *smem_flag = (atom_add_acq_rel_gpu(&p.sk_counters[tile], 1u) == (unsigned)S - 1u) ? 1 : 0;
   asm volatile("bar.sync 1, 128;" ::: "memory");
   if (*smem_flag == 0) return false;
-  __threadfence();
-  if (threadIdx.x == 64) p.sk_counters[tile] = 0u;  // every CTA of this tile has taken its ticket
+  if (threadIdx.x == 64) st_relaxed_gpu_u32(&p.sk_counters[tile], 0u);  // every CTA of this tile has taken its ticket
   if (col >= 0) {
     const size_t stride = (size_t)p.M * p.sk_width;
 #pragma unroll

@@ -42,13 +42,14 @@ def _u16(t):
     return t.contiguous().view(torch.int16).numpy().astype(np.uint16)
 
 
-@pytest.mark.parametrize("family,grid,dims,temp,n_fwd", [
-    ("llama", 3, (256, 512), 0.0, 3),     # K = 256 / 512: 8 rows per job, one slot (gate|up: 8 pairs, two slots)
-    ("qwen", 2, (256, 512), 0.8, 3),      # q/k norm, head_dim 128, Philox sampling inside the kernel
-    ("llama", 3, (256, 4096), 0.0, 2),    # down-proj K = 4096: 4 rows x 2 segments per job
-    ("llama", 2, (256, 5120), 0.7, 2),    # down-proj K = 5120: 2 rows x 4 segments per job
+@pytest.mark.parametrize("family,grid,dims,temp,n_fwd,n,bs", [
+    ("llama", 3, (256, 512), 0.0, 3, 21, 16),     # K = 256 / 512: 8 rows per job, one slot (gate|up: 8 pairs, two slots)
+    ("qwen", 2, (256, 512), 0.8, 3, 270, 64),     # q/k norm, head_dim 128, Philox sampling in the kernel; context > 256:
+                                                  # two KV splits per head, partials + ticket + merge by the last split
+    ("llama", 3, (256, 4096), 0.0, 2, 21, 16),    # down-proj K = 4096: 4 rows x 2 segments per job
+    ("llama", 2, (256, 5120), 0.7, 2, 21, 16),    # down-proj K = 5120: 2 rows x 4 segments per job
 ])
-def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims, temp, n_fwd):
+def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims, temp, n_fwd, n, bs):
     from oracle import verify as V
     _build()
     torch.manual_seed(1)
@@ -56,12 +57,11 @@ def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims
     hidden, ffn = dims
     heads = hidden // hd if family == "llama" else max(2, hidden // hd)
     cfg = ModelCfg(hidden=hidden, layers=2, heads=heads, kv_heads=max(1, heads // 2), head_dim=hd, ffn=ffn, vocab=264,
-                   max_pos=256, rms_eps=1e-5 if family == "llama" else 1e-6, rope_theta=500000.0, qk_norm=(family != "llama"))
+                   max_pos=512, rms_eps=1e-5 if family == "llama" else 1e-6, rope_theta=500000.0, qk_norm=(family != "llama"))
     w = random_weights(cfg, seed=9)
-    bs, nblk = 16, 6
+    nblk = 6
     model = OracleModel(cfg, w, num_blocks=nblk, block_size=bs)
     bt = [4, 1, 5, 0, 3, 2]
-    n = 21
     prompt = torch.randint(0, cfg.vocab, (n,))
     slots = torch.tensor([bt[p // bs] * bs + p % bs for p in range(n)], dtype=torch.int32)
     btt = torch.tensor([bt], dtype=torch.int32)

@@ -93,7 +93,7 @@ def test_spec_steps_match_oracle(family, use_graph):
 
 # golden steps (of 10, two sequences each) that must be reproduced EXACTLY — speculations, accept counts and recovery
 # tokens of both sequences — before any near-tie may end the comparison; measured on B200 (profiles/r02_pytest_gpu.txt)
-MIN_EXACT_GOLDEN_STEPS = {"llama": 1, "qwen": 1}
+MIN_EXACT_GOLDEN_STEPS = {"llama": 2, "qwen": 4}
 
 
 @pytest.mark.parametrize("family", ["llama", "qwen"])

@@ -26,7 +26,9 @@ DIMS = {
 }
 
 
-def _rank_main(rank, world, port, use_graph, use_symm, q, dims="small"):
+def _rank_main(rank, world, port, use_graph, use_symm, q, dims="small", fused_publish="0"):
+    import os
+    os.environ["SSDK_FUSED_PUBLISH"] = fused_publish  # read once per process by libssdk
     import torch.distributed as dist
     from oracle.model import ModelCfg, OracleModel, random_weights
     from oracle.spec import SpecSession, check_greedy_step, contiguous_block_tables
@@ -93,16 +95,19 @@ def _rank_main(rank, world, port, use_graph, use_symm, q, dims="small"):
         q.put((rank, "fail", traceback.format_exc(), None))
 
 
-@pytest.mark.parametrize("use_graph,use_symm,dims", [(False, False, "small"), (True, False, "small"), (False, True, "small"),
-                                                     (True, True, "small"), (True, True, "wide"), (False, True, "wide")])
-def test_tp2_spec_steps(use_graph, use_symm, dims):
+@pytest.mark.parametrize("use_graph,use_symm,dims,fused", [
+    (False, False, "small", "0"), (True, False, "small", "0"), (False, True, "small", "0"), (True, True, "small", "0"),
+    (True, True, "wide", "0"), (False, True, "wide", "0"),
+    (True, True, "small", "1"), (True, True, "wide", "1"), (False, True, "wide", "1"),  # GEMM-epilogue publish (EPI_PUBLISH)
+])
+def test_tp2_spec_steps(use_graph, use_symm, dims, fused):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, use_graph, use_symm, q, dims)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, use_graph, use_symm, q, dims, fused)) for r in range(2)]
     for p in procs:
         p.start()
     res = {}

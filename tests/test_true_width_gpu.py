@@ -7,12 +7,13 @@ a pure integer function of (stream, row, column) and are regenerated here bit-fo
 the C-ABI (ssdk_forward_tokens / ssdk_spec_step):
   * the first sampled token, every speculated token, accept count and recovery token: EXACT (all margins are in the
     thousands by construction, so there is no near-tie to excuse a mismatch);
-  * logits_p / logits_q at 2048 sampled vocabulary columns of every row: |diff| <= 1.5 + 2^-5 |ref| everywhere AND a mean
-    |diff| <= 0.6 (bf16 logits of magnitude 70-90, whose spacing is 0.5; measured on B200: mean |diff| 0.37 for the 70B
-    widths, less for the others, i.e. the two implementations round most logits to the same or a neighbouring bf16 value
-    after K = 8192 / 28672 accumulations in different orders; measured with the oracle: switching
-    the attention branch or the MLP branch off moves the target's sampled logits by 9 on average (max 64), the 1B-width
-    draft's by 2 on average — far outside both bounds);
+  * logits_p / logits_q at 2048 sampled vocabulary columns of every row: |diff| <= 2.5 + 2^-5 |ref| everywhere AND a mean
+    |diff| <= 0.6.  Calibration of these bounds (bf16 logits of magnitude 70-90, spacing 0.5): the oracle's OWN two
+    arithmetic variants — Inductor single-rounding vs eager double-rounding norms / SiLU, oracle/ops.py `compiled` —
+    differ from each other by mean 0.127 / max 1.0 (8B widths) and mean 0.348 / max 2.0 (70B widths); this engine against
+    the oracle measures mean 0.138 (8B), 0.178 (Qwen3-32B), 0.376 / max 1.7 (70B) on B200: the same one-ulp noise.  A real
+    defect is far outside: switching the attention branch or the MLP branch off moves the target's sampled logits by 9 on
+    average (max 64), the 1B-width draft's by 2 on average;
   * the top-1 logit of every row within 2^-6 relative.
 """
 import numpy as np
@@ -58,7 +59,7 @@ def _run(name: str):
             got = eng[..., cols].float().cpu()
             want = bf16(z[f"s{st}_{tag}"]).float()
             err = (got - want).abs()
-            tol = 1.5 + want.abs() / 32
+            tol = 2.5 + want.abs() / 32
             ratio = err / tol
             i = int(ratio.argmax())
             assert float(ratio.max()) <= 1.0, (f"{name} step {st} {tag}: |diff| {float(err.flatten()[i]):.2f} at |ref| "
