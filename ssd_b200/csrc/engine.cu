@@ -147,13 +147,13 @@ static int launch_rope(Launcher& L, int M, const RopeParams& rp) {
     default: return fail("unsupported head_dim %d for RoPE (64, 128 and 256 are built)", rp.head_dim);
   }
 }
-static int umma_n_for(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : 64); }
+static int umma_n_for(int M) { return M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256))); }
 
-static int auto_splits(int tiles, int num_kb) {
+static int auto_splits(int tiles, int num_kb, int ctas_per_sm = 2) {
   // Fill the machine in ONE wave: 2 CTAs/SM are resident (shared-memory bound), so tiles * S <= 2 * #SM; a partial
   // second wave doubles the kernel time (measured: 320 CTAs on 296 slots ran at 65 % of the HBM peak).  S <= 8 keeps
   // the consumers' split-K reduction to one batch of loads; >= 4 k-blocks per CTA keeps the TMA pipeline busy.
-  const int slots = 2 * num_sms();
+  const int slots = ctas_per_sm * num_sms();
   int S = std::max(1, slots / tiles);
   S = std::min(S, std::max(1, num_kb / 4));
   S = std::min(S, 8);
@@ -179,6 +179,8 @@ static int launch_gemm(Launcher& L, int umma_n, int epi, const CUtensorMap& tmW,
   SSDK_GEMM_CASE(16, EPI_BF16) SSDK_GEMM_CASE(16, EPI_PARTIAL) SSDK_GEMM_CASE(16, EPI_SILU) SSDK_GEMM_CASE(16, EPI_PUBLISH)
   SSDK_GEMM_CASE(32, EPI_BF16) SSDK_GEMM_CASE(32, EPI_PARTIAL) SSDK_GEMM_CASE(32, EPI_SILU) SSDK_GEMM_CASE(32, EPI_PUBLISH)
   SSDK_GEMM_CASE(64, EPI_BF16) SSDK_GEMM_CASE(64, EPI_PARTIAL) SSDK_GEMM_CASE(64, EPI_SILU) SSDK_GEMM_CASE(64, EPI_PUBLISH)
+  SSDK_GEMM_CASE(128, EPI_BF16) SSDK_GEMM_CASE(128, EPI_PARTIAL) SSDK_GEMM_CASE(128, EPI_SILU)
+  SSDK_GEMM_CASE(256, EPI_BF16) SSDK_GEMM_CASE(256, EPI_PARTIAL) SSDK_GEMM_CASE(256, EPI_SILU)
 #undef SSDK_GEMM_CASE
   return fail("no GEMM instance for umma_n=%d epi=%d", umma_n, epi);
 }
@@ -197,8 +199,10 @@ static int weight_tmap(WeightMat& w) {
   return 0;
 }
 
-// activations buffers usable as the X operand: [kMaxTokens rows, K] bf16
-constexpr int kMaxTokens = 64;
+// activations buffers usable as the X operand: [kMaxTokens rows, K] bf16.  Decode / verify steps use <= 64 tokens
+// (UMMA N 16 / 32 / 64); prefill chunks and larger batches up to 256 (UMMA N 128 / 256: the weights are then streamed once
+// per 256 tokens instead of once per 64 — a 2k-token 70B prompt reads 139 GB 8 times instead of 32).
+constexpr int kMaxTokens = 256;
 struct XMapCache {
   std::map<std::tuple<const void*, int, int>, CUtensorMap> maps;
   int get(const void* ptr, int K, int umma_n, const CUtensorMap** out) {
@@ -401,7 +405,7 @@ static int64_t carve(ssdk_engine* e, uint8_t* base) {
   w.samp_partial = (ArgMax*)take((size_t)kMaxTokens * kSampleChunks * sizeof(ArgMax));
   w.samp_counters = (unsigned*)take(kMaxTokens * 4);
   w.ver_rows = (RowPart*)take((size_t)kVerifyMaxRows * kVerifyCtas * sizeof(RowPart));
-  w.ver_rec = (RecPart*)take((size_t)16 * kVerifyCtas * sizeof(RecPart));
+  w.ver_rec = (RecPart*)take((size_t)kVerifyMaxBatch * kVerifyCtas * sizeof(RecPart));
   w.ver_counters = (unsigned*)take(64);
   w.ds_vec = (bf16*)take((size_t)(qmax + 4 * dmax + fmax + Hmax * hdmax + 64) * 2);
   w.ds_attn = (float*)take((size_t)Hmax * kDsSplits * (hdmax + 2) * 4);
@@ -501,7 +505,7 @@ static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w
   if (epi == EPI_SILU) {
     tiles = (N_out + 63) / 64;
     // narrow (tensor-parallel) shards: too few 64-column tiles to fill the machine -> split K, reduced inside the kernel
-    splits = (tiles < num_sms() && out != nullptr && e->ws.partials) ? auto_splits(tiles, p.num_kb) : 1;
+    splits = (un <= 64 && tiles < num_sms() && out != nullptr && e->ws.partials) ? auto_splits(tiles, p.num_kb) : 1;
     if (splits > 1 && (tiles > 512 || (size_t)splits * M * 2 * N_out > e->ws.partial_floats)) splits = 1;
     p.tile_rows = 64;
     p.hi_row_offset = N_out;
@@ -510,12 +514,13 @@ static int enqueue_gemm(ssdk_engine* e, Launcher& L, const bf16* x, WeightMat& w
     }
   } else {
     tiles = (N_out + kTileRows - 1) / kTileRows;
-    splits = (epi == EPI_PARTIAL || epi == EPI_PUBLISH) ? auto_splits(tiles, p.num_kb) : 1;
+    splits = (epi == EPI_PARTIAL || epi == EPI_PUBLISH) ? auto_splits(tiles, p.num_kb, un <= 64 ? 2 : 1) : 1;
     p.tile_rows = kTileRows;
     p.hi_row_offset = 64;
   }
   if (epi == EPI_PUBLISH) {
     if (!pub) return fail("EPI_PUBLISH without publish parameters");
+    if (un > 64) return fail("EPI_PUBLISH is planned for <= 64 tokens");
     if (tiles > 512) return fail("EPI_PUBLISH: %d tiles > 512 ticket counters", tiles);
     if ((size_t)splits * M * N_out > e->ws.partial_floats) return fail("split-K partial buffer too small");
     p.pub = *pub;
@@ -691,7 +696,7 @@ static int enqueue_forward(ssdk_engine* e, Launcher& L, const Fwd& f) {
                           w.att_lse, w.att_counters, f.B, f.Q, m.H, m.KV, m.hd, bs, mb, scale, TQ, MT, nqt, nsplit));
 
     // ---- output projection (row-parallel) ----
-    const bool fuse_pub = use_symm && fused_publish_enabled();
+    const bool fuse_pub = use_symm && fused_publish_enabled() && M <= 64;
     GemmOut oproj;
     bool oproj_symm = false;
     int oproj_idx = 0;
@@ -1056,6 +1061,8 @@ static int init_kernel_attrs() {
   SSDK_ATTR_G(16, EPI_BF16) SSDK_ATTR_G(16, EPI_PARTIAL) SSDK_ATTR_G(16, EPI_SILU) SSDK_ATTR_G(16, EPI_PUBLISH)
   SSDK_ATTR_G(32, EPI_BF16) SSDK_ATTR_G(32, EPI_PARTIAL) SSDK_ATTR_G(32, EPI_SILU) SSDK_ATTR_G(32, EPI_PUBLISH)
   SSDK_ATTR_G(64, EPI_BF16) SSDK_ATTR_G(64, EPI_PARTIAL) SSDK_ATTR_G(64, EPI_SILU) SSDK_ATTR_G(64, EPI_PUBLISH)
+  SSDK_ATTR_G(128, EPI_BF16) SSDK_ATTR_G(128, EPI_PARTIAL) SSDK_ATTR_G(128, EPI_SILU)
+  SSDK_ATTR_G(256, EPI_BF16) SSDK_ATTR_G(256, EPI_PARTIAL) SSDK_ATTR_G(256, EPI_SILU)
 #undef SSDK_ATTR_G
 #define SSDK_ATTR_A(HD, MT) \
   CK(cudaFuncSetAttribute(paged_attn_kernel<HD, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 2 * kAttChunk * (HD + 8) * 2));
@@ -1089,8 +1096,8 @@ int ssdk_create(const ssdk_model_cfg* target, const ssdk_model_cfg* draft, const
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("ssdk_create: no CUDA device");
   if (rt->spec_k < 0 || rt->spec_k > 7) return fail("spec_k=%d out of range [0,7]", rt->spec_k);
-  if (rt->max_batch < 1 || rt->max_batch * (rt->spec_k + 1) > kMaxTokens || rt->max_batch > 16)
-    return fail("max_batch=%d: need max_batch*(K+1) <= %d and max_batch <= 16", rt->max_batch, kMaxTokens);
+  if (rt->max_batch < 1 || rt->max_batch * (rt->spec_k + 1) > kMaxTokens || rt->max_batch > kVerifyMaxBatch)
+    return fail("max_batch=%d: need max_batch*(K+1) <= %d and max_batch <= %d", rt->max_batch, kMaxTokens, kVerifyMaxBatch);
   if (rt->spec_k > 0 && !draft && target->tp_rank == 0) return fail("spec_k>0 needs a draft model on rank 0");
   ssdk_engine* e = new ssdk_engine();
   e->rt = *rt;
@@ -1410,7 +1417,7 @@ int ssdk_forward_tokens(ssdk_handle h, int which, int batch, int q_len, const in
   }
   uint8_t* pin = h->pin_fw + (size_t)slot * h->fw_slot_bytes;
   memcpy(pin + h->off_ctx, ctx_len, (size_t)batch * 4);
-  float zero[16] = {0};
+  float zero[kVerifyMaxBatch] = {0};
   memcpy(pin + h->off_tt, temps ? temps : zero, (size_t)batch * 4);
   uint64_t ss[2] = {seed, step_id};
   memcpy(pin + h->off_seed, ss, 16);
@@ -1485,7 +1492,7 @@ int ssdk_gemm_small_m(const void* x, const void* w, void* y, float* partials, in
   CKI(make_tmap(&tmX, x, M, K, un));
   const int tiles = (N + kTileRows - 1) / kTileRows;
   const int num_kb = K / kBlockK;
-  int S = split_k > 0 ? std::min(split_k, num_kb) : auto_splits(tiles, num_kb);
+  int S = split_k > 0 ? std::min(split_k, num_kb) : auto_splits(tiles, num_kb, un <= 64 ? 2 : 1);
   if (S > 1 && !partials) return fail("gemm_small_m: split_k=%d needs a partials buffer", S);
   GemmParams p;
   p.M = M; p.N = N; p.ldo = ldy; p.num_kb = num_kb; p.tile_rows = kTileRows; p.hi_row_offset = 64;
@@ -1608,7 +1615,7 @@ int64_t ssdk_verify_scratch_bytes(int B, int K) {
 int ssdk_verify(const void* logits_p, const void* logits_q, const int64_t* speculations, const float* temps_t,
                 const float* temps_q, const int32_t* cache_hits, int jit_speculate, int B, int K, int V, uint64_t seed,
                 uint64_t step_id, int32_t* n_accept, int64_t* recovery, void* scratch, void* stream) {
-  if (B < 1 || B > 16 || K < 1 || B * (2 * K + 1) > kVerifyMaxRows) return fail("verify: B=%d K=%d out of range", B, K);
+  if (B < 1 || B > kVerifyMaxBatch || K < 1 || B * (2 * K + 1) > kVerifyMaxRows) return fail("verify: B=%d K=%d out of range", B, K);
   Launcher L;
   L.st = (cudaStream_t)stream;
   // counters live in the first 1 KB of the scratch and must be zero on entry

@@ -110,15 +110,19 @@ SSDK_DEVINL bool splitk_ticket_reduce(uint32_t* r, const GemmParams& p, int col,
 template <int UMMA_N>
 struct GemmCfg {
   static constexpr int kABytes = kTileRows * kBlockK * 2;  // 16384
-  static constexpr int kBBytes = UMMA_N * kBlockK * 2;     // 2048 / 4096 / 8192
+  static constexpr int kBBytes = UMMA_N * kBlockK * 2;     // 2048 / 4096 / 8192 / 16384 / 32768
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (UMMA_N == 16) ? 6 : (UMMA_N == 32 ? 5 : 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
-  static constexpr int kTmemCols = (UMMA_N <= 32) ? 32 : 64;
+  static constexpr int kTmemCols = (UMMA_N <= 32) ? 32 : UMMA_N;   // power of two >= 32
+  // UMMA_N <= 64 (decode / verify: weight streaming, two CTAs per SM keep ~190 KB of loads in flight); 128 / 256 (prefill
+  // chunks and large batches: 128-192 KB of stages, one CTA per SM, the weights are read once per 128 / 256 tokens)
+  static constexpr int kCtasPerSm = UMMA_N <= 64 ? 2 : 1;
+  static constexpr int kEpiCols = UMMA_N < 64 ? UMMA_N : 64;       // accumulator columns handled per epilogue pass
 };
 
 template <int UMMA_N, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 2)
+__global__ void __launch_bounds__(kGemmThreads, GemmCfg<UMMA_N>::kCtasPerSm)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, GemmParams p) {
   using Cfg = GemmCfg<UMMA_N>;
   constexpr int kStages = Cfg::kStages;
@@ -224,9 +228,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) trace_fine(TRF_GEMM + 0);  // CTA 0's accumulator complete
-    uint32_t r[UMMA_N];
+    constexpr int CW = Cfg::kEpiCols;
+    // the accumulator is drained in passes of CW token columns (one pass for UMMA_N <= 64); token index = m0 + m
+    for (int m0 = 0; m0 < UMMA_N && m0 < p.M; m0 += CW) {
+    uint32_t r[CW];
 #pragma unroll
-    for (int c = 0; c < UMMA_N / 16; ++c) tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(q * 32) << 16) + c * 16, r + c * 16);
+    for (int c = 0; c < CW / 16; ++c) tmem_ld_32x32b_x16(tmem_d + ((uint32_t)(q * 32) << 16) + m0 + c * 16, r + c * 16);
     tmem_ld_wait();
 
     if (EPI == EPI_BF16) {
@@ -234,34 +241,35 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
       if (n < p.N) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll
-        for (int m = 0; m < UMMA_N; ++m)
-          if (m < p.M) out[(size_t)m * p.ldo + n] = f2bf(__uint_as_float(r[m]));
+        for (int m = 0; m < CW; ++m)
+          if (m0 + m < p.M) out[(size_t)(m0 + m) * p.ldo + n] = f2bf(__uint_as_float(r[m]));
       }
     } else if (EPI == EPI_PARTIAL) {
       const int n = row_lo + row;
       if (n < p.N) {
         float* out = reinterpret_cast<float*>(p.out) + (size_t)blockIdx.y * p.M * p.N;
 #pragma unroll
-        for (int m = 0; m < UMMA_N; ++m)
-          if (m < p.M) out[(size_t)m * p.N + n] = __uint_as_float(r[m]);
+        for (int m = 0; m < CW; ++m)
+          if (m0 + m < p.M) out[(size_t)(m0 + m) * p.N + n] = __uint_as_float(r[m]);
       }
     } else if (EPI == EPI_PUBLISH) {
       const PublishParams& pb = p.pub;
       const int n = row_lo + row;
-      const bool last = splitk_ticket_reduce<UMMA_N>(r, p, n < p.N ? n : -1, tile, &pub_last);
+      // in-kernel split-K (ticket) is only planned for single-pass shapes (UMMA_N <= 64: decode / verify)
+      const bool last = splitk_ticket_reduce<CW>(r, p, n < p.N ? n : -1, tile, &pub_last);
       if (last) {
         const unsigned seq = __ldcg(pb.fwd_seq);
         const unsigned e = symm_epoch_of(seq, pb.call_idx);
         const size_t slot_off = ((size_t)symm_parity_of(seq, pb.call_idx, pb.n_calls) * kPubMaxRanks + pb.rank) * pb.slot_bytes;
 #pragma unroll
-        for (int m = 0; m < UMMA_N; ++m) {
-          if (m < p.M) {
+        for (int m = 0; m < CW; ++m) {
+          if (m0 + m < p.M) {
             const __nv_bfloat16 mine = f2bf(__uint_as_float(r[m]));
             const uint32_t bits = (uint32_t)__bfloat16_as_ushort(mine);
             const uint32_t nb = __shfl_down_sync(0xffffffffu, bits, 1);
             if ((lane & 1) == 0 && n < p.N) {
               const uint2 word = make_uint2(bits | (nb << 16), e);
-              const size_t off = slot_off + (((size_t)m * p.N + n) >> 1) * 8;
+              const size_t off = slot_off + (((size_t)(m0 + m) * p.N + n) >> 1) * 8;
 #pragma unroll
               for (int rk = 0; rk < kPubMaxRanks; ++rk)
                 if (rk < pb.n_ranks) st_global_v2_u32(pb.peer[rk] + off, word.x, word.y);  // ONE 8-byte store: data + flag
@@ -277,17 +285,18 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const int j = row & 63;
         const int ncol = row_lo + j;
         const int col = ncol < p.N ? (row < 64 ? ncol : p.N + ncol) : -1;
-        if (!splitk_ticket_reduce<UMMA_N>(r, p, col, tile, &pub_last)) goto epilogue_done;
+        if (!splitk_ticket_reduce<CW>(r, p, col, tile, &pub_last)) goto epilogue_done;
       }
-      // All MMAs have retired (tmem_full), so pipeline stage 0 is free to stage the exchange.
+      // All MMAs have retired (tmem_full), so the pipeline stages are free to stage the exchange (128 x (CW + 1) floats).
       float* ex = reinterpret_cast<float*>(smem);
-      constexpr int LD = UMMA_N + 1;
+      constexpr int LD = CW + 1;
 #pragma unroll
-      for (int m = 0; m < UMMA_N; ++m) ex[row * LD + m] = __uint_as_float(r[m]);
+      for (int m = 0; m < CW; ++m) ex[row * LD + m] = __uint_as_float(r[m]);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int e = threadIdx.x - 64;  // 0..127
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-      for (int idx = e; idx < 64 * p.M; idx += 128) {
+      const int mc = min(CW, p.M - m0);
+      for (int idx = e; idx < 64 * mc; idx += 128) {
         const int j = idx & 63, m = idx >> 6;
         const int n = row_lo + j;
         if (n < p.N) {
@@ -295,10 +304,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
           const float g = bf16_round(ex[j * LD + m]);
           const float u = bf16_round(ex[(64 + j) * LD + m]);
           const float h = (g / (1.0f + __expf(-g))) * u;
-          out[(size_t)m * p.ldo + n] = f2bf(h);
+          out[(size_t)(m0 + m) * p.ldo + n] = f2bf(h);
         }
       }
+      if (UMMA_N > CW) asm volatile("bar.sync 1, 128;" ::: "memory");  // the next pass overwrites the exchange buffer
     }
+    }  // accumulator passes
   }
 
 epilogue_done:

@@ -160,7 +160,8 @@ struct VerifyParams {
 };
 
 constexpr int kVerifyThreads = 128;
-constexpr int kVerifyMaxRows = 16 * 15;  // B*(2K+1) bound for the smem row table (B<=16 at K=7)
+constexpr int kVerifyMaxBatch = 32;                    // sequences per verify launch
+constexpr int kVerifyMaxRows = kVerifyMaxBatch * 15;  // B*(2K+1) bound for the smem row table (K <= 7)
 
 SSDK_DEVINL void online_merge(float& m, float& s, float m2, float s2) {
   if (m2 == -INFINITY) return;
@@ -181,9 +182,9 @@ __global__ void __launch_bounds__(kVerifyThreads) verify_kernel(VerifyParams p) 
   SSDK_STATIC_SMEM(int, row_arg, kVerifyMaxRows);
   SSDK_STATIC_SMEM(float, row_m, kVerifyMaxRows);
   SSDK_STATIC_SMEM(float, row_z, kVerifyMaxRows);
-  SSDK_STATIC_SMEM(int, s_n, 16);      // accepted count
-  SSDK_STATIC_SMEM(int, s_flags, 16);  // bit0 = needs recovery draw, bit1 = adjust
-  SSDK_STATIC_SMEM(long long, s_rec_greedy, 16);
+  SSDK_STATIC_SMEM(int, s_n, kVerifyMaxBatch);      // accepted count
+  SSDK_STATIC_SMEM(int, s_flags, kVerifyMaxBatch);  // bit0 = needs recovery draw, bit1 = adjust
+  SSDK_STATIC_SMEM(long long, s_rec_greedy, kVerifyMaxBatch);
   SSDK_SHARED_VAR(bool, is_last);
   pdl_launch_dependents();
   pdl_wait();

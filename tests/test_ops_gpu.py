@@ -25,6 +25,8 @@ def _ref_linear(x, w):
     (1, 512, 128, 1), (7, 512, 128, 1), (7, 3072, 2048, 1), (1, 3072, 2048, 0), (7, 4096, 4096, 0),
     (16, 2048, 8192, 0), (7, 4096, 4096, 3), (33, 1024, 512, 1), (64, 1280, 1024, 0), (7, 16032, 2048, 1),
     (5, 200, 64, 1), (7, 2048, 8192, 8), (7, 1024, 4096, 16), (20, 1024, 2048, 4), (40, 512, 1024, 2),
+    # prefill chunks / large batches: UMMA N = 128 and 256 (accumulator drained in passes of 64 token columns)
+    (65, 1024, 512, 1), (128, 3072, 2048, 0), (200, 2048, 8192, 0), (256, 4096, 4096, 1), (129, 640, 1024, 2), (256, 512, 256, 1),
 ])
 def test_linear_matches_fp64(dev, M, N, K, split):
     from ssd_b200 import ops
@@ -42,7 +44,8 @@ def test_linear_matches_fp64(dev, M, N, K, split):
     assert ulp_mismatch_fraction(y.cpu(), y32.cpu()) < 0.02
 
 
-@pytest.mark.parametrize("M,ffn,K", [(1, 256, 128), (7, 8192, 2048), (7, 1024, 512), (40, 512, 256), (3, 200, 128)])
+@pytest.mark.parametrize("M,ffn,K", [(1, 256, 128), (7, 8192, 2048), (7, 1024, 512), (40, 512, 256), (3, 200, 128),
+                                     (100, 1024, 512), (256, 2048, 1024), (130, 14336, 4096)])
 def test_gate_up_silu(dev, M, ffn, K):
     from oracle import ops as O
     from ssd_b200 import ops
@@ -56,7 +59,7 @@ def test_gate_up_silu(dev, M, ffn, K):
     assert ulp_mismatch_fraction(h, ref) < 0.05
 
 
-@pytest.mark.parametrize("M,d", [(1, 128), (7, 2048), (7, 8192), (64, 4096), (3, 5120)])
+@pytest.mark.parametrize("M,d", [(1, 128), (7, 2048), (7, 8192), (64, 4096), (3, 5120), (256, 4096)])
 def test_rms_norm(dev, M, d):
     from oracle import ops as O
     from ssd_b200 import ops
@@ -116,14 +119,14 @@ def test_rope_store_kv(dev, H, KV, hd, qk_norm):
 
 @pytest.mark.parametrize("H,KV,hd", [(4, 1, 64), (32, 8, 64), (32, 8, 128), (8, 1, 128), (16, 8, 128), (2, 2, 64)])
 @pytest.mark.parametrize("q_len,ctx", [(1, [1]), (1, [63, 300]), (7, [7]), (7, [64, 65]), (5, [1000, 257]), (40, [40]),
-                                       (64, [200])])
+                                       (64, [200]), (200, [200]), (256, [700]), (100, [100, 356])])
 def test_paged_attention(dev, H, KV, hd, q_len, ctx):
     from oracle import ops as O
     from ssd_b200 import ops
     g = torch.Generator().manual_seed(H + KV + hd + q_len + sum(ctx))
     B, bs = len(ctx), 256
-    if B * q_len > 64:
-        pytest.skip("more than 64 query tokens")
+    if B * q_len > 256:
+        pytest.skip("more than 256 query tokens")
     mb = (max(ctx) + bs - 1) // bs + 1
     nblk = B * mb + 2
     kc = torch.randn(nblk, bs, KV, hd, generator=g).to(torch.bfloat16)
