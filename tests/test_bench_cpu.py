@@ -30,3 +30,44 @@ def test_reference_arm_prints_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_usable_cores_respects_affinity_and_cgroup_quota():
+    sys.path.insert(0, ROOT)
+    import bench
+    n = bench.usable_cores()
+    assert 1 <= n <= len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            assert n <= max(1, int(int(quota) / int(period)))
+    except FileNotFoundError:
+        pass
+
+
+def test_synthetic_pair_construction():
+    """The synthetic target / draft pair of the bench: both next-token maps are permutations (every greedy decision has a
+    full margin), they agree on ~alpha of the tokens, the hash generator is a pure function of (stream, row, column), and
+    the closed-form accept length matches a simulation of the chain the bench's parity_check walks."""
+    import torch
+    sys.path.insert(0, ROOT)
+    from ssd_b200 import synth
+    V, alpha, K = 20000, 0.85, 6
+    pi_t, pi_d = synth.permutations(V, 0, alpha, "cpu")
+    assert sorted(pi_t.tolist()) == list(range(V)) and sorted(pi_d.tolist()) == list(range(V))
+    agree = (pi_t == pi_d).float().mean().item()
+    assert abs(agree - alpha) < 0.02
+    a = synth.hash_uniform(64, 256, 0.02, 5, "cpu")
+    b = synth.hash_uniform(16, 256, 0.02, 5, "cpu", row0=48)
+    assert torch.equal(a[48:], b) and abs(a.float().std().item() - 0.02) < 2e-3 and abs(a.float().mean().item()) < 1e-3
+    assert not torch.equal(a, synth.hash_uniform(64, 256, 0.02, 6, "cpu"))
+    # simulate sync SD on the chain: tokens per step = 1 + accepted prefix (truncated at K)
+    tok, total, steps = 17, 0, 4000
+    for _ in range(steps):
+        n, cur = 0, tok
+        while n < K and int(pi_d[cur]) == int(pi_t[cur]):
+            cur = int(pi_t[cur])
+            n += 1
+        total += n + 1
+        tok = int(pi_t[cur])  # the recovery token = the target's choice after the last accepted one
+    assert abs(total / steps - synth.expected_tokens_per_step(alpha, K)) < 0.15
