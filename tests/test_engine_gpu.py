@@ -209,3 +209,48 @@ def test_streaming_draft_kernel_matches_kernel_per_op_path():
                              text=True, timeout=1500)
         print(res.stdout[-600:])
         assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("chunk", [32, 64, 256])
+def test_long_prompt_prefill_in_unsynchronised_chunks(chunk):
+    """ssdk_forward_tokens does not synchronise for non-final prefill chunks, so its pinned staging must not be
+    reused before the queued H2D copy has run.  A 450-token prompt goes through 15 / 8 / 2 chunks (the first ones without a
+    host sync); the sampled token and the last-position logits must match the oracle's single-pass prefill, and the KV it
+    left behind must carry a correct decode step."""
+    from oracle.model import ModelCfg, OracleModel, random_weights
+    from oracle.spec import SpecSession, contiguous_block_tables
+    from ssd_b200 import lib as L
+    from ssd_b200.runner import PairRunner
+    dev = torch.device("cuda:0")
+    K, bs, mb = 4, 64, 8
+    tc = ModelCfg(hidden=256, layers=2, heads=4, kv_heads=2, head_dim=64, ffn=512, vocab=1024, max_pos=512)
+    dc = ModelCfg(**{**tc.__dict__, "layers": 1})
+    wt = random_weights(tc, 23)
+    wd = {"embed": wt["embed"], "lm_head": wt["lm_head"], "final_norm": wt["final_norm"], "layers": [wt["layers"][0]]}
+    r = PairRunner(_spec(tc), _spec(dc), spec_k=K, max_batch=1, block_size=bs, max_model_len=bs * mb, use_graph=True)
+    r.bind_weights(L.TARGET, _to_dev(wt, dev))
+    r.bind_weights(L.DRAFT, _to_dev(wd, dev))
+    r.finalize()
+    g = torch.Generator().manual_seed(99)
+    prompt = torch.randint(0, tc.vocab, (450,), generator=g).tolist()
+    bt = contiguous_block_tables(1, mb)
+    s = SpecSession(OracleModel(tc, wt, mb, bs), OracleModel(dc, wd, mb, bs), K, mb)
+    rec_o = s.prefill([prompt], [0.0], bt, bt.clone())
+    rec = r.prefill(L.TARGET, prompt, bt[0].tolist(), chunk=chunk)
+    r.prefill(L.DRAFT, prompt, bt[0].tolist(), want_sample=False, chunk=chunk)
+    # oracle logits of the last prompt position (teacher-forced single pass) vs the engine's
+    ids = torch.tensor(prompt, dtype=torch.int64)
+    o2 = OracleModel(tc, wt, mb, bs)
+    h = SpecSession(o2, None, K, mb)._forward(o2, ids, [0], len(prompt), bt)
+    want = o2.compute_logits(h[-1:])[0].float()
+    got = r.logits_last(1)[0].float().cpu()
+    torch.testing.assert_close(got, want, atol=0.08, rtol=0.03)
+    margin = float(want.topk(2).values[0] - want.topk(2).values[1])
+    assert rec == rec_o[0] or margin < EPS, (rec, rec_o, margin)
+    # the KV written by the chunks carries a correct speculative step
+    from oracle.spec import check_greedy_step
+    toks, nacc, nrec = r.spec_step([len(prompt)], [rec_o[0]], [bt[0].tolist()], [bt[0].tolist()], [0.0], [0.0])
+    lp, lq = s.spec_step_forced(torch.from_numpy(toks))
+    hard, _ = check_greedy_step(torch.from_numpy(toks), nacc.tolist(), nrec.tolist(), lp, lq, EPS)
+    assert not hard, hard
+    r.close()
