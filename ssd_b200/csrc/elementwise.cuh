@@ -387,9 +387,13 @@ __global__ void __launch_bounds__(256) ar_publish_kernel(ArPublishParams p) {
     }
     const uint4 v = pack_bf16x8(x);
     const uint4 lo = make_uint4(v.x, e, v.y, e), hi = make_uint4(v.z, e, v.w, e);
+    // gridDim.y == 1: every thread pushes its words to all ranks; gridDim.y == n_ranks: CTA column y serves peer y only —
+    // the (cheap, L2-resident) reduction is repeated per peer, the NVLink stores of the 8 peers are issued from 8x as many
+    // SMs instead of back to back from one thread
+    const int r_lo = gridDim.y > 1 ? (int)blockIdx.y : 0, r_hi = gridDim.y > 1 ? (int)blockIdx.y + 1 : p.n_ranks;
 #pragma unroll
     for (int r = 0; r < kSymmMaxRanks; ++r) {
-      if (r < p.n_ranks) {
+      if (r >= r_lo && r < r_hi) {
         uint4* dst = reinterpret_cast<uint4*>(p.peer[r] + slot_off) + idx / 4;
         dst[0] = lo;
         dst[1] = hi;

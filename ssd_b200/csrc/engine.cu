@@ -55,6 +55,11 @@ static int fail(const char* fmt, ...) {
     if (_r != 0) return _r;       \
   } while (0)
 
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
 // ------------------------------------------------------------------------------------------
 // launch helper (optional programmatic dependent launch)
 // ------------------------------------------------------------------------------------------
@@ -562,7 +567,12 @@ static int enqueue_ar_publish(ssdk_engine* e, Launcher& L, const GemmOut* x, con
   ap.slot_bytes = e->symm_slot_bytes;
   ap.fwd_seq = e->ws.ar_state; ap.call_idx = call_idx; ap.n_calls = 2 * m.cfg.layers + 1;
   const int n8 = M * d / 8;
-  return L.go(ar_publish_kernel, dim3(std::max(1, std::min((n8 + 255) / 256, num_sms()))), dim3(256), 0, ap);
+  // one CTA column per destination rank (see ar_publish_kernel): default at 8 ranks, where it measured 12.20 vs 12.57 ms/step
+  // (Llama-3.1-70B TP=8); SSDK_PUBLISH_PER_PEER=0/1 overrides
+  static int per_peer = -1;
+  if (per_peer < 0) per_peer = env_int("SSDK_PUBLISH_PER_PEER", e->symm_n >= 8 ? 1 : 0) != 0 ? 1 : 0;
+  const int gx = std::max(1, std::min((n8 + 255) / 256, num_sms()));
+  return L.go(ar_publish_kernel, dim3(gx, per_peer ? e->symm_n : 1), dim3(256), 0, ap);
 }
 
 // row-parallel GEMM whose epilogue publishes the rank's bf16 result to every peer (EPI_PUBLISH)
@@ -842,10 +852,6 @@ __global__ void advance_kernel(int32_t* __restrict__ ctx, int64_t* __restrict__ 
 // streaming draft kernel: the K+1 draft forwards + K samplings of a step in ONE cooperative launch (draft_stream.cuh)
 // SSDK_DRAFT_STREAM=0 keeps the kernel-per-op path; SSDK_DRAFT_L2_AHEAD=n: L2 window of n jobs per CTA beyond the ring.
 // ------------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return (s && *s) ? atoi(s) : dflt;
-}
 static bool draft_stream_enabled() {
   static int v = -1;
   if (v < 0) v = env_int("SSDK_DRAFT_STREAM", 1) != 0 ? 1 : 0;
