@@ -71,6 +71,13 @@ class Config:
             self.max_model_len = min(self.max_model_len, self.draft_hf_config.max_position_embeddings)
         if self.max_num_batched_tokens < self.max_model_len:
             raise AssertionError("max_num_batched_tokens < max_model_len (config.py:94)")
+        # limits of libssdk (DESIGN.md "Limits"), reported here rather than at the first step
+        k1 = (self.speculate_k + 1) if self.speculate else 1
+        if self.speculate and not 1 <= self.speculate_k <= 7:
+            raise ValueError(f"speculate_k={self.speculate_k}: libssdk supports 1 <= k <= 7")
+        if self.max_num_seqs > 32 or self.max_num_seqs * k1 > 256:
+            raise ValueError(f"max_num_seqs={self.max_num_seqs} with {k1} tokens per sequence and step: libssdk runs at most 32 "
+                             "sequences and 256 tokens per step")
 
 
 class _HFConfig:

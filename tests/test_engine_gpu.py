@@ -254,3 +254,52 @@ def test_long_prompt_prefill_in_unsynchronised_chunks(chunk):
     hard, _ = check_greedy_step(torch.from_numpy(toks), nacc.tolist(), nrec.tolist(), lp, lq, EPS)
     assert not hard, hard
     r.close()
+
+
+def test_large_batch_spec_steps_match_oracle():
+    """20 sequences x (K+1 = 7) = 140 tokens per verify forward: the UMMA N = 256 instances of the GEMM inside the step graph,
+    verify_kernel beyond 16 sequences, the kernel-per-op draft at M = 20.  Decisions checked against the oracle with the
+    near-tie protocol; logits within tolerance."""
+    from oracle.model import ModelCfg, OracleModel, random_weights
+    from oracle.spec import SpecSession, check_greedy_step, contiguous_block_tables
+    from ssd_b200 import lib as L
+    from ssd_b200.runner import PairRunner
+    dev = torch.device("cuda:0")
+    B, K, bs, mb = 20, 6, 64, 2
+    tc = ModelCfg(hidden=256, layers=2, heads=4, kv_heads=2, head_dim=64, ffn=512, vocab=1024, max_pos=256)
+    dc = ModelCfg(**{**tc.__dict__, "layers": 1})
+    wt = random_weights(tc, 31)
+    wd = {"embed": wt["embed"], "lm_head": wt["lm_head"], "final_norm": wt["final_norm"], "layers": [wt["layers"][0]]}
+    r = PairRunner(_spec(tc), _spec(dc), spec_k=K, max_batch=B, block_size=bs, max_model_len=bs * mb, use_graph=True)
+    r.bind_weights(L.TARGET, _to_dev(wt, dev))
+    r.bind_weights(L.DRAFT, _to_dev(wd, dev))
+    r.finalize()
+    g = torch.Generator().manual_seed(7)
+    prompts = [torch.randint(0, tc.vocab, (int(n),), generator=g).tolist() for n in torch.randint(3, 40, (B,), generator=g)]
+    bt = contiguous_block_tables(B, mb)
+    bts = [bt[b].tolist() for b in range(B)]
+    s = SpecSession(OracleModel(tc, wt, B * mb, bs), OracleModel(dc, wd, B * mb, bs), K, mb)
+    rec_o = s.prefill(prompts, [0.0] * B, bt, bt.clone())
+    rec = []
+    for b in range(B):
+        rec.append(r.prefill(L.TARGET, prompts[b], bts[b]))
+        r.prefill(L.DRAFT, prompts[b], bts[b], want_sample=False)
+    assert sum(int(a != b_) for a, b_ in zip(rec, rec_o)) <= 1  # a bf16 near-tie may flip one first token
+    rec = list(rec_o)
+    ctx = [len(p) for p in prompts]
+    soft_total = 0
+    for step in range(3):
+        toks, nacc, nrec = r.spec_step(ctx, rec, bts, bts, [0.0] * B, [0.0] * B)
+        spec = torch.from_numpy(toks)
+        assert spec[:, 0].tolist() == rec
+        lp_o, lq_o = s.spec_step_forced(spec)
+        torch.testing.assert_close(r.logits_p(B).cpu().float(), lp_o.float(), atol=0.08, rtol=0.03)
+        torch.testing.assert_close(r.logits_q(B).cpu().float(), lq_o.float(), atol=0.08, rtol=0.03)
+        hard, soft = check_greedy_step(spec, nacc.tolist(), nrec.tolist(), lp_o, lq_o, EPS)
+        assert not hard, f"step {step}: {hard}"
+        soft_total += len(soft)
+        ctx = [c + int(n) + 1 for c, n in zip(ctx, nacc)]
+        rec = nrec.tolist()
+        s.advance(nacc.tolist(), rec)
+    assert soft_total <= 12
+    r.close()
