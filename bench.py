@@ -110,7 +110,7 @@ def usable_cores() -> int:
     return max(1, n)
 
 
-def run_reference_gpu_subprocess(args, timeout_s: int = 900):
+def run_reference_gpu_subprocess(args, timeout_s: int = 480):
     """bench.py --impl reference-gpu / the `reference_gpu` object of the default line: baseline/ref_gpu.py in its own
     process (the reference calls os._exit from an atexit hook, and both engines cannot hold a 70B model at once)."""
     out_path = os.path.join(tempfile.mkdtemp(prefix="ssd_refgpu_"), "ref.json")
