@@ -428,6 +428,10 @@ SSDK_DEVINL void mbar_arrive(uint64_t* bar) {
   emu_mbar_settle(w);
   *bar = w;
 }
+SSDK_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  std::lock_guard<std::mutex> g(emu_mbar_mu());
+  return (uint32_t)(*bar >> 63) != parity;
+}
 SSDK_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (;;) {
     {

@@ -208,11 +208,11 @@ SSDK_DEVINL void ds_producer(const DsParams& p, const DsGeom* geom, uint8_t* rin
   DsCursor c;
   c.f = 0; c.l = 0; c.m = DS_QKV; c.s = (int)blockIdx.x; c.valid = p.n_fwd > 0;
   ds_cursor_settle(p, geom, c);
-  DsCursor a = c;  // L2 window: stays l2_ahead jobs in front of c
-  for (int i = 0; i < p.l2_ahead && a.valid; ++i) {
-    if (i >= 3) ds_prefetch_job(p, geom, a);  // the first jobs go to shared memory right away
-    ds_cursor_next(p, geom, a);
-  }
+  // Optional L2 window (l2_ahead > 0): `a` = c + `ahead` jobs.  It moves ONLY while this CTA's demand stream is idle — the
+  // ring is full and the newest bulk copy has landed (attention phase, device-wide barriers, prologues) — so that HBM keeps
+  // streaming the next matrices into L2 without ever queueing in front of a demand load.
+  DsCursor a = c;
+  int ahead = 0;
   unsigned n = 0;  // slots requested so far
   const unsigned S = (unsigned)p.n_slots;
   while (c.valid) {
@@ -222,18 +222,30 @@ SSDK_DEVINL void ds_producer(const DsParams& p, const DsGeom* geom, uint8_t* rin
     const unsigned bytes = (unsigned)rows * (unsigned)g.K * 2u;
     const int parts = g.kind == DS_PAIR ? 2 : 1;
     for (int q = 0; q < parts; ++q) {
-      const unsigned slot = n % S, round = n / S;
-      mbar_wait(&empty[slot], (round & 1u) ^ 1u);  // a fresh barrier passes the first round at once
+      const unsigned slot = n % S, par = ((n / S) & 1u) ^ 1u;  // a fresh barrier passes the first round at once
+      if (p.l2_ahead > 0 && n > 0) {
+        // poll the slot; whenever everything requested so far has landed, move the L2 window one job on.  Once the window
+        // is full the bounded wait below takes over.
+        const long long t0 = clock64();
+        while (ahead < p.l2_ahead && a.valid && !mbar_try_wait(&empty[slot], par)) {
+          if ((ahead > 0 || q == 0) && mbar_try_wait(&full[(n - 1u) % S], ((n - 1u) / S) & 1u)) {
+            ds_prefetch_job(p, geom, a);
+            ds_cursor_next(p, geom, a);
+            ++ahead;
+          } else if ((q != 0 && ahead == 0) || clock64() - t0 > 2000000000LL) {
+            break;  // (a stuck protocol ends in mbar_wait's trap)
+          }
+        }
+      }
+      mbar_wait(&empty[slot], par);
       mbar_arrive_expect_tx(&full[slot], bytes);
       const __nv_bfloat16* src = w + ((size_t)(q ? g.rows : 0) + (size_t)c.s * g.rpj) * g.K;
       bulk_load_g2s(ring + (size_t)slot * kDsSlotBytes, src, bytes, &full[slot]);
       ++n;
     }
     ds_cursor_next(p, geom, c);
-    if (p.l2_ahead > 0 && a.valid) {
-      ds_prefetch_job(p, geom, a);
-      ds_cursor_next(p, geom, a);
-    }
+    if (ahead > 0) --ahead;
+    else a = c;
   }
 }
 
@@ -402,15 +414,32 @@ SSDK_DEVINL float ds_block_sum(float v, float* red) {  // all consumer threads g
 
 // xs[i] = bf16r( r_i * rsqrt(mean r^2 + eps) * w_i ),  r = a (+ b) in fp32;  resid_out = bf16(r) (written by CTA 0 only).
 // a / b are L2-resident vectors produced by earlier phases.  d is a multiple of 8.
+// The operands of a norm prologue that do NOT depend on the phase that just ended — the norm weight (first touch of a layer:
+// an HBM miss) and the residual written one phase earlier — are requested BEFORE the device-wide barrier and ride it out in
+// registers (first 8-element slice of the thread; d > 8 * kDsConsumers loads the rest inside the prologue).
+struct DsPre {
+  uint4 w, b;
+};
+SSDK_DEVINL DsPre ds_preload(const __nv_bfloat16* b, const __nv_bfloat16* w, int d) {
+  DsPre r;
+  const int i = threadIdx.x * 8;
+  r.w = r.b = make_uint4(0u, 0u, 0u, 0u);
+  if (i < d) {
+    r.w = *reinterpret_cast<const uint4*>(w + i);
+    if (b) r.b = ds_ldcg16(b + i);
+  }
+  return r;
+}
 SSDK_DEVINL void ds_norm_prologue(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* resid_out,
-                                  const __nv_bfloat16* w, float eps, int d, float* xs, float* red) {
+                                  const __nv_bfloat16* w, float eps, int d, float* xs, float* red, const DsPre* pre) {
   float ss = 0.f;
-  for (int i = threadIdx.x * 8; i < d; i += kDsConsumers * 8) {
+  const int i0 = threadIdx.x * 8;
+  for (int i = i0; i < d; i += kDsConsumers * 8) {
     float x[8];
     unpack_bf16x8(ds_ldcg16(a + i), x);
     if (b) {
       float y[8];
-      unpack_bf16x8(ds_ldcg16(b + i), y);
+      unpack_bf16x8((pre && i == i0) ? pre->b : ds_ldcg16(b + i), y);
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] += y[j];
     }
@@ -423,9 +452,9 @@ SSDK_DEVINL void ds_norm_prologue(const __nv_bfloat16* a, const __nv_bfloat16* b
   }
   ss = ds_block_sum(ss, red);
   const float rstd = rsqrtf(ss / (float)d + eps);
-  for (int i = threadIdx.x * 8; i < d; i += kDsConsumers * 8) {
+  for (int i = i0; i < d; i += kDsConsumers * 8) {
     float wv[8];
-    unpack_bf16x8(*reinterpret_cast<const uint4*>(w + i), wv);
+    unpack_bf16x8((pre && i == i0) ? pre->w : *reinterpret_cast<const uint4*>(w + i), wv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) xs[i + j] = bf16_round(xs[i + j] * rstd * wv[j]);
   }
@@ -746,14 +775,15 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
     const int ctx = ctx_base + f + 1;  // tokens visible to this forward, the new one included
     const __nv_bfloat16* emb = p.embed + (size_t)tok * p.d;
     int cur = 0;  // resid[cur] holds the residual entering the layer (layer 0: the embedding row itself)
+    DsPre pre;    // operands of the next norm prologue, requested before the barrier in front of it
     for (int l = 0; l < p.L; ++l) {
       const DsLayer& lw = p.layers[l];
       // ---- A: (add +) input norm -> q|k|v ----
       if (l == 0) {
         // first layer: hidden = norm(embed), residual = embed (models/llama3.py:192-193)
-        ds_norm_prologue(emb, nullptr, resid[cur ^ 1], lw.in_norm, p.eps, p.d, xs, red);
+        ds_norm_prologue(emb, nullptr, resid[cur ^ 1], lw.in_norm, p.eps, p.d, xs, red, nullptr);
       } else {
-        ds_norm_prologue(p.vec_down, resid[cur], resid[cur ^ 1], lw.in_norm, p.eps, p.d, xs, red);
+        ds_norm_prologue(p.vec_down, resid[cur], resid[cur ^ 1], lw.in_norm, p.eps, p.d, xs, red, &pre);
       }
       cur ^= 1;
       ds_mark(f, 0);
@@ -776,10 +806,11 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
       ds_load_vec(p.vec_attn, p.H * HD, xs);
       ds_consume(ring, geom[DS_O], xs, res, p.vec_o);
       ds_mark(f, 5);
+      pre = ds_preload(resid[cur], lw.post_norm, p.d);
       bar.sync();
       ds_mark(f, 6);
       // ---- D: add + post-attention norm -> gate|up with SiLU*mul ----
-      ds_norm_prologue(p.vec_o, resid[cur], resid[cur ^ 1], lw.post_norm, p.eps, p.d, xs, red);
+      ds_norm_prologue(p.vec_o, resid[cur], resid[cur ^ 1], lw.post_norm, p.eps, p.d, xs, red, &pre);
       cur ^= 1;
       ds_mark(f, 7);
       ds_consume_pair(ring, geom[DS_GU], xs, p.vec_act);
@@ -790,12 +821,13 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
       ds_load_vec(p.vec_act, p.ffn, xs);
       ds_consume(ring, geom[DS_DOWN], xs, res, p.vec_down);
       ds_mark(f, 10);
+      pre = ds_preload(resid[cur], l + 1 < p.L ? p.layers[l + 1].in_norm : p.final_norm, p.d);
       bar.sync();
       ds_mark(f, 11);
     }
     if (!ds_has_head(p, f)) break;
     // ---- final add + norm (models/llama3.py:198) -> lm_head; logits rounded to bf16 like every linear output ----
-    ds_norm_prologue(p.vec_down, resid[cur], nullptr, p.final_norm, p.eps, p.d, xs, red);
+    ds_norm_prologue(p.vec_down, resid[cur], nullptr, p.final_norm, p.eps, p.d, xs, red, &pre);
     DsSample smp;
     smp.greedy = (T == 0.f);
     smp.invT = smp.greedy ? 1.f : 1.f / T;

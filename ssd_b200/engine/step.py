@@ -33,11 +33,9 @@ class AutoRegressiveStep(InferenceStep):
         self.runner, self.tokenizer, self.seed = runner, tokenizer, seed
 
     def prefill(self, seqs) -> int:
-        toks = []
-        for seq in seqs:
-            toks.append(self.runner.prefill(L.TARGET, seq.token_ids, seq.block_table, start=seq.num_cached_tokens
-                                            if seq.num_cached_tokens < len(seq) else len(seq) - 1,
-                                            temp=seq.temperature, seed=self.seed))
+        toks = self.runner.prefill_many(L.TARGET, [s.token_ids for s in seqs], [s.block_table for s in seqs],
+                                        [min(s.num_cached_tokens, len(s) - 1) for s in seqs],
+                                        [s.temperature for s in seqs], seed=self.seed)
         self.scheduler.postprocess(seqs, toks, True)
         return sum(len(s) for s in seqs)
 
@@ -58,13 +56,15 @@ class SpecDecodeStep(InferenceStep):
     def prefill(self, seqs) -> int:
         """Target prefill samples the first recovery token (verifier.py:32-52), then the draft caches the prompt
         (speculator_sync.py:14-23).  Prefix-cache hits skip the cached blocks (scheduler.py:71-72)."""
-        for seq in seqs:
-            n = len(seq)
-            t0 = min(seq.num_cached_tokens, n - 1)  # always run at least the last token to get logits
-            d0 = min(seq.num_draft_cached_tokens, n - 1)
-            seq.recovery_token_id = self.runner.prefill(L.TARGET, seq.token_ids, seq.block_table, start=t0,
-                                                        temp=seq.temperature, seed=self.seed)
-            self.runner.prefill(L.DRAFT, seq.token_ids, seq.draft_block_table, start=d0, want_sample=False)
+        ids = [s.token_ids for s in seqs]
+        # always run at least the last token to get logits
+        rec = self.runner.prefill_many(L.TARGET, ids, [s.block_table for s in seqs],
+                                       [min(s.num_cached_tokens, len(s) - 1) for s in seqs],
+                                       [s.temperature for s in seqs], seed=self.seed)
+        self.runner.prefill_many(L.DRAFT, ids, [s.draft_block_table for s in seqs],
+                                 [min(s.num_draft_cached_tokens, len(s) - 1) for s in seqs], want_sample=False)
+        for seq, r in zip(seqs, rec):
+            seq.recovery_token_id = r
             seq.num_cached_tokens = seq.num_prompt_tokens
             seq.num_draft_cached_tokens = seq.num_prompt_tokens
         return sum(len(s) for s in seqs)

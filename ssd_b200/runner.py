@@ -196,6 +196,54 @@ class PairRunner:
             pos += q
         return tok[0] if tok else None
 
+    @staticmethod
+    def plan_prefill_call(remaining: list[int], max_tokens: int, max_batch: int) -> tuple[list[int], int]:
+        """Pick the sequences and the (uniform) chunk length of the next prefill call: among the groups made of the nb
+        sequences with the most tokens left, the one that covers the most tokens under nb * q <= max_tokens.  Equal-length
+        prompts (the reference bench: 16 x 128 tokens) pack two to a 256-token call; ragged ones degrade to one at a time."""
+        order = sorted((i for i, r in enumerate(remaining) if r > 0), key=lambda i: (-remaining[i], i))
+        best, best_q = [], 0
+        for nb in range(1, min(len(order), max_batch) + 1):
+            q = min(max_tokens // nb, remaining[order[nb - 1]])
+            if q < 1:
+                break
+            if nb * q > len(best) * best_q:
+                best, best_q = order[:nb], q
+        return sorted(best), best_q
+
+    def prefill_many(self, which: int, tokens: list[list[int]], block_tables: list[list[int]], starts: list[int],
+                     temps: list[float] | None = None, want_sample: bool = True, chunk: int = 256, seed: int = 0):
+        """Prefill several sequences (runner_helpers.py:123-180 batches them by cu_seqlens): every call carries up to
+        `chunk` tokens of up to max_batch sequences, the same number of tokens from each (plan_prefill_call), through the
+        multi-query path; a sequence's first token is sampled by the call that holds its last prompt token.  Returns one
+        token per sequence (None without want_sample)."""
+        n = len(tokens)
+        pos = list(starts)
+        temps = list(temps) if temps is not None else [0.0] * n
+        out: list[int | None] = [None] * n
+        # A prefix-cache hit (start > 0) reads pages that an EARLIER sequence of the same batch may still be writing
+        # (block_manager hashes a block when it is allocated, the reference stores the whole batch's K/V before any
+        # attention runs): only sequences that compute their whole prompt share calls; the hits follow one by one, in order.
+        packed = [i for i in range(n) if starts[i] == 0]
+        while True:
+            idx, q = self.plan_prefill_call([len(tokens[i]) - pos[i] if i in packed else 0 for i in range(n)],
+                                            min(chunk, 256), self.max_batch)
+            if not idx:
+                break
+            done = [pos[i] + q == len(tokens[i]) for i in idx]
+            toks = self.forward_tokens(which, [tokens[i][pos[i]:pos[i] + q] for i in idx], [pos[i] for i in idx],
+                                       [block_tables[i] for i in idx], [temps[i] for i in idx],
+                                       want_sample=(want_sample and any(done)), seed=seed)
+            for j, i in enumerate(idx):
+                pos[i] += q
+                if done[j] and toks is not None:
+                    out[i] = toks[j]
+        for i in range(n):
+            if starts[i] != 0:
+                out[i] = self.prefill(which, tokens[i], block_tables[i], start=starts[i], temp=temps[i],
+                                      want_sample=want_sample, chunk=chunk, seed=seed)
+        return out if want_sample else None
+
     def spec_step(self, ctx_len: list[int], recovery: list[int], bt_target, bt_draft, temps_t: list[float],
                   temps_q: list[float], seed: int = 0):
         """One sync speculative step.  Returns (speculations [B,K+1], n_accept [B], recovery [B]) as numpy."""

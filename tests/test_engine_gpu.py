@@ -303,3 +303,54 @@ def test_large_batch_spec_steps_match_oracle():
         s.advance(nacc.tolist(), rec)
     assert soft_total <= 12
     r.close()
+
+
+def test_packed_prefill_of_ragged_prompts_matches_oracle():
+    """prefill_many: several prompts per call (uniform chunk per call, sizes planned on the host), ragged lengths incl. equal
+    pairs and a 1-token prompt.  First tokens against the oracle (near-tie protocol), last-position logits of the sequences
+    in the final call within tolerance, and the KV it wrote must carry two speculative steps for the whole batch."""
+    from oracle.model import ModelCfg, OracleModel, random_weights
+    from oracle.spec import SpecSession, check_greedy_step, contiguous_block_tables
+    from ssd_b200 import lib as L
+    from ssd_b200.runner import PairRunner
+    dev = torch.device("cuda:0")
+    lens = [100, 100, 37, 1, 180, 64, 100, 9]
+    B, K, bs, mb = len(lens), 4, 64, 4
+    tc = ModelCfg(hidden=256, layers=2, heads=4, kv_heads=2, head_dim=64, ffn=512, vocab=1024, max_pos=256)
+    dc = ModelCfg(**{**tc.__dict__, "layers": 1})
+    wt = random_weights(tc, 41)
+    wd = {"embed": wt["embed"], "lm_head": wt["lm_head"], "final_norm": wt["final_norm"], "layers": [wt["layers"][0]]}
+    r = PairRunner(_spec(tc), _spec(dc), spec_k=K, max_batch=B, block_size=bs, max_model_len=bs * mb, use_graph=True)
+    r.bind_weights(L.TARGET, _to_dev(wt, dev))
+    r.bind_weights(L.DRAFT, _to_dev(wd, dev))
+    r.finalize()
+    g = torch.Generator().manual_seed(17)
+    prompts = [torch.randint(0, tc.vocab, (n,), generator=g).tolist() for n in lens]
+    bt = contiguous_block_tables(B, mb)
+    bts = [bt[b].tolist() for b in range(B)]
+    s = SpecSession(OracleModel(tc, wt, B * mb, bs), OracleModel(dc, wd, B * mb, bs), K, mb)
+    rec_o = s.prefill(prompts, [0.0] * B, bt, bt.clone())
+    calls = []
+    fwd = r.forward_tokens
+    r.forward_tokens = lambda which, ids, *a, **k: (calls.append((which, len(ids), len(ids[0]))), fwd(which, ids, *a, **k))[1]
+    rec = r.prefill_many(L.TARGET, prompts, bts, [0] * B)
+    r.prefill_many(L.DRAFT, prompts, bts, [0] * B, want_sample=False)
+    r.forward_tokens = fwd
+    tgt_calls = [c for c in calls if c[0] == L.TARGET]
+    assert sum(b * q for _, b, q in tgt_calls) == sum(lens) and max(b for _, b, _ in tgt_calls) > 1
+    assert len(tgt_calls) < len(lens), tgt_calls  # fewer weight passes than one per prompt
+    assert sum(int(a != b_) for a, b_ in zip(rec, rec_o)) <= 1, (rec, rec_o)
+    rec = list(rec_o)
+    ctx = list(lens)
+    for step in range(2):
+        toks, nacc, nrec = r.spec_step(ctx, rec, bts, bts, [0.0] * B, [0.0] * B)
+        spec = torch.from_numpy(toks)
+        lp_o, lq_o = s.spec_step_forced(spec)
+        torch.testing.assert_close(r.logits_p(B).cpu().float(), lp_o.float(), atol=0.08, rtol=0.03)
+        torch.testing.assert_close(r.logits_q(B).cpu().float(), lq_o.float(), atol=0.08, rtol=0.03)
+        hard, _ = check_greedy_step(spec, nacc.tolist(), nrec.tolist(), lp_o, lq_o, EPS)
+        assert not hard, f"step {step}: {hard}"
+        ctx = [c + int(n) + 1 for c, n in zip(ctx, nacc)]
+        rec = nrec.tolist()
+        s.advance(nacc.tolist(), rec)
+    r.close()

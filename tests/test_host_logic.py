@@ -166,3 +166,51 @@ def test_compat_shim_exposes_reference_names():
         assert k in METRICS
     assert hasattr(P, "DATASET_PATHS") and hasattr(P, "HF_CACHE_DIR") and hasattr(P, "EAGLE3_QWEN_32B")
     assert SP().temperature == 1.0 and SP().max_new_tokens == 256 and SP().draft_temperature is None
+
+
+def test_prefill_call_planner_packs_equal_prompts_and_never_loses_tokens():
+    """PairRunner.plan_prefill_call / prefill_many (host side of the varlen prefill, runner_helpers.py:123-180): every
+    prompt token is run exactly once and in order, a call never exceeds the token or batch limit, equal-length prompts
+    share calls, and prefix-cache hits are kept out of the shared calls (their pages may still be in flight)."""
+    from ssd_b200.runner import PairRunner
+
+    class Rec:
+        max_batch = 8
+        plan_prefill_call = staticmethod(PairRunner.plan_prefill_call)
+        prefill_many = PairRunner.prefill_many
+        prefill = PairRunner.prefill
+
+        def __init__(self):
+            self.calls = []
+
+        def forward_tokens(self, which, ids, ctx_len, block_tables, temps=None, want_sample=True, seed=0):
+            assert len(ids) <= self.max_batch and len(ids) * len(ids[0]) <= 256 and len({len(x) for x in ids}) == 1
+            self.calls.append((ids, list(ctx_len), [bt[0] for bt in block_tables], want_sample))
+            return [x[-1] + 1000 for x in ids] if want_sample else None
+
+    assert PairRunner.plan_prefill_call([128] * 16, 256, 32) == ([0, 1], 128)
+    assert PairRunner.plan_prefill_call([300, 40, 30], 256, 32) == ([0], 256)
+    assert PairRunner.plan_prefill_call([44, 40, 30], 256, 32) == ([0, 1, 2], 30)
+    assert PairRunner.plan_prefill_call([0, 0], 256, 32) == ([], 0)
+    assert PairRunner.plan_prefill_call([5] * 40, 256, 8)[0] == list(range(8))
+
+    rng = random.Random(3)
+    for trial in range(20):
+        n = rng.randint(1, 12)
+        lens = [rng.choice([1, 7, 128, 128, 300, 517]) for _ in range(n)]
+        starts = [rng.choice([0, 0, 0, min(256, l - 1)]) for l in lens]
+        toks = [[i * 10000 + j for j in range(l)] for i, l in enumerate(lens)]
+        r = Rec()
+        out = r.prefill_many(0, toks, [[i] for i in range(n)], starts, want_sample=True)
+        assert out == [t[-1] + 1000 for t in toks]
+        seen = {i: starts[i] for i in range(n)}
+        for ids, ctx, owners, _ in r.calls:
+            if len(ids) > 1:
+                assert all(starts[o] == 0 for o in owners), "a prefix-cache hit shared a call"
+            for row, c, o in zip(ids, ctx, owners):
+                assert c == seen[o] and row == toks[o][c:c + len(row)]
+                seen[o] += len(row)
+        assert all(seen[i] == lens[i] for i in range(n))
+    r = Rec()
+    r.prefill_many(0, [list(range(128))] * 16, [[i] for i in range(16)], [0] * 16)
+    assert len(r.calls) == 8

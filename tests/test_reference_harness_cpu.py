@@ -39,6 +39,10 @@ class FakeRunner:
         assert len(block_table) * 256 >= len(tokens), "prefill without enough KV blocks"
         return _next(tokens[-1]) if want_sample else None
 
+    def prefill_many(self, which, tokens, block_tables, starts, temps=None, want_sample=True, chunk=256, seed=0):
+        out = [self.prefill(which, t, bt, start=s, want_sample=want_sample) for t, bt, s in zip(tokens, block_tables, starts)]
+        return out if want_sample else None
+
     def forward_tokens(self, which, ids, ctx_len, block_tables, temps=None, want_sample=True, seed=0):
         self.calls["decode"] += 1
         return [_next(x[-1]) for x in ids]
