@@ -203,9 +203,6 @@ SSDK_DEVINL void bulk_load_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
       ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictFirst)
       : "memory");
 }
-SSDK_DEVINL void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
 
 // ----------------------------------------------------------------------------------
 // PTX: tcgen05 (5th-gen tensor cores) + TMEM
@@ -449,7 +446,6 @@ SSDK_DEVINL void bulk_load_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
   emu_mbar_settle(w);
   *bar = w;
 }
-SSDK_DEVINL void bulk_prefetch_l2(const void*, uint32_t) {}
 SSDK_DEVINL uint4 ld_volatile_v4(const void* p) {
   // two aligned 8-byte words {2 x bf16, epoch}: each is read atomically, like the device's 8-byte store granularity
   const uint64_t* q = reinterpret_cast<const uint64_t*>(p);

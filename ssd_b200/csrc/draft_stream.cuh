@@ -77,7 +77,6 @@ struct DsParams {
   unsigned* bar_state;           // one 64-bit arrival counter (8-byte aligned), only ever grows; zero before the first launch
   unsigned* attn_ticket;         // [KV] arrival tickets of the split-KV units, zero between phases
   int n_slots;                   // ring depth (3 .. kDsMaxSlots)
-  int l2_ahead;                  // jobs requested into L2 beyond the ones in flight to shared memory (0 = off)
   DsLayer layers[kDsMaxLayers];
 };
 
@@ -188,31 +187,17 @@ SSDK_DEVINL void ds_cursor_settle(const DsParams& p, const DsGeom* geom, DsCurso
   }
 }
 
-// the producer: one lane walks the job sequence of this CTA and refills slots as the consumers release them.  Optionally
-// a second cursor runs l2_ahead jobs in front and only pulls those bytes into L2 (fire-and-forget): when the consumers sit
-// in a phase without weights (attention) or at a barrier, the ring is full and HBM would idle; the L2 window keeps it busy
-// and the later copies into shared memory hit L2.
+// the producer: one lane walks the job sequence of this CTA and refills slots as the consumers release them.  (An L2
+// window beyond the ring — `cp.async.bulk.prefetch.L2` of the next jobs, continuously or only while every requested copy
+// had landed — was measured twice and removed: 8B + 1B 8.53 / 8.63 vs 8.34 / 8.48 ms per step, profiles/r02_draft_stream.md.)
 SSDK_DEVINL void ds_cursor_next(const DsParams& p, const DsGeom* geom, DsCursor& c) {
   c.s += (int)gridDim.x;
   if (c.s >= geom[c.m].nj) ds_cursor_settle(p, geom, c);
-}
-SSDK_DEVINL void ds_prefetch_job(const DsParams& p, const DsGeom* geom, const DsCursor& c) {
-  const DsGeom g = geom[c.m];
-  const __nv_bfloat16* w = ds_weight(p, c.l, c.m);
-  const int rows = min(g.rpj, g.rows - c.s * g.rpj);
-  const unsigned bytes = (unsigned)rows * (unsigned)g.K * 2u;
-  bulk_prefetch_l2(w + (size_t)c.s * g.rpj * g.K, bytes);
-  if (g.kind == DS_PAIR) bulk_prefetch_l2(w + ((size_t)g.rows + (size_t)c.s * g.rpj) * g.K, bytes);
 }
 SSDK_DEVINL void ds_producer(const DsParams& p, const DsGeom* geom, uint8_t* ring, uint64_t* full, uint64_t* empty) {
   DsCursor c;
   c.f = 0; c.l = 0; c.m = DS_QKV; c.s = (int)blockIdx.x; c.valid = p.n_fwd > 0;
   ds_cursor_settle(p, geom, c);
-  // Optional L2 window (l2_ahead > 0): `a` = c + `ahead` jobs.  It moves ONLY while this CTA's demand stream is idle — the
-  // ring is full and the newest bulk copy has landed (attention phase, device-wide barriers, prologues) — so that HBM keeps
-  // streaming the next matrices into L2 without ever queueing in front of a demand load.
-  DsCursor a = c;
-  int ahead = 0;
   unsigned n = 0;  // slots requested so far
   const unsigned S = (unsigned)p.n_slots;
   while (c.valid) {
@@ -222,30 +207,14 @@ SSDK_DEVINL void ds_producer(const DsParams& p, const DsGeom* geom, uint8_t* rin
     const unsigned bytes = (unsigned)rows * (unsigned)g.K * 2u;
     const int parts = g.kind == DS_PAIR ? 2 : 1;
     for (int q = 0; q < parts; ++q) {
-      const unsigned slot = n % S, par = ((n / S) & 1u) ^ 1u;  // a fresh barrier passes the first round at once
-      if (p.l2_ahead > 0 && n > 0) {
-        // poll the slot; whenever everything requested so far has landed, move the L2 window one job on.  Once the window
-        // is full the bounded wait below takes over.
-        const long long t0 = clock64();
-        while (ahead < p.l2_ahead && a.valid && !mbar_try_wait(&empty[slot], par)) {
-          if ((ahead > 0 || q == 0) && mbar_try_wait(&full[(n - 1u) % S], ((n - 1u) / S) & 1u)) {
-            ds_prefetch_job(p, geom, a);
-            ds_cursor_next(p, geom, a);
-            ++ahead;
-          } else if ((q != 0 && ahead == 0) || clock64() - t0 > 2000000000LL) {
-            break;  // (a stuck protocol ends in mbar_wait's trap)
-          }
-        }
-      }
-      mbar_wait(&empty[slot], par);
+      const unsigned slot = n % S, round = n / S;
+      mbar_wait(&empty[slot], (round & 1u) ^ 1u);  // a fresh barrier passes the first round at once
       mbar_arrive_expect_tx(&full[slot], bytes);
       const __nv_bfloat16* src = w + ((size_t)(q ? g.rows : 0) + (size_t)c.s * g.rpj) * g.K;
       bulk_load_g2s(ring + (size_t)slot * kDsSlotBytes, src, bytes, &full[slot]);
       ++n;
     }
     ds_cursor_next(p, geom, c);
-    if (ahead > 0) --ahead;
-    else a = c;
   }
 }
 

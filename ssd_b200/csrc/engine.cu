@@ -850,7 +850,7 @@ __global__ void advance_kernel(int32_t* __restrict__ ctx, int64_t* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------
 // streaming draft kernel: the K+1 draft forwards + K samplings of a step in ONE cooperative launch (draft_stream.cuh)
-// SSDK_DRAFT_STREAM=0 keeps the kernel-per-op path; SSDK_DRAFT_L2_AHEAD=n: L2 window of n jobs per CTA beyond the ring.
+// SSDK_DRAFT_STREAM=0 keeps the kernel-per-op path.
 // ------------------------------------------------------------------------------------------
 static bool draft_stream_enabled() {
   static int v = -1;
@@ -933,7 +933,6 @@ static int enqueue_draft_stream(ssdk_engine* e, Launcher& L, int64_t* tok_buf, i
   p.bar_state = w.ds_sync;
   p.attn_ticket = w.ds_sync + 8;
   p.n_slots = ds_ring_slots(m);
-  p.l2_ahead = std::max(0, env_int("SSDK_DRAFT_L2_AHEAD", 0));
   for (int l = 0; l < p.L; ++l) {
     const LayerW& lw = m.layers[l];
     p.layers[l] = DsLayer{lw.qkv.ptr, lw.o.ptr, lw.gate_up.ptr, lw.down.ptr, lw.input_norm, lw.post_norm, lw.q_norm, lw.k_norm};

@@ -96,7 +96,7 @@ int main(int argc, char** argv) {
   p.samp_partial = partial.data();
   p.bar_state = sync;
   p.attn_ticket = sync + 8;
-  p.n_slots = n_stages; p.l2_ahead = 4;
+  p.n_slots = n_stages;
   for (int l = 0; l < L; ++l)
     p.layers[l] = ssdk::DsLayer{lw[l].qkv.data(), lw[l].o.data(), lw[l].gate_up.data(), lw[l].down.data(),
                                 lw[l].in_norm.data(), lw[l].post_norm.data(), lw[l].q_norm.data(), lw[l].k_norm.data()};
