@@ -48,6 +48,7 @@ constexpr int kDsSplits = 8;          // KV splits per kv head in phase B
 constexpr int kDsSlotBytes = 32768;   // one ring slot
 constexpr int kDsMaxSlots = 6;
 constexpr int kDsMaxSteps = 8;        // 256-column steps per K segment (segment <= 2048 columns)
+constexpr int kDsBtSmem = 32;         // page-table entries staged in shared memory at kernel start (the table is launch-constant)
 
 struct DsLayer {
   const __nv_bfloat16 *qkv, *o, *gate_up, *down, *in_norm, *post_norm, *q_norm, *k_norm;
@@ -450,10 +451,47 @@ SSDK_DEVINL void ds_load_vec(const __nv_bfloat16* v, int n, float* xs) {
 // attractive — no partials, ticket or merge below 256 — but the token loop is a chain of dependent L2 round trips per
 // iteration: measured 8B + 1B 10.29 vs 8.34 ms/step.)
 SSDK_DEVINL int ds_num_splits(int ctx) { return min(kDsSplits, max(1, (ctx + 7) >> 3)); }
+// page of token t: from the shared-memory copy of the (launch-constant) page table when it fits, else from global memory
+SSDK_DEVINL int ds_page_of(const DsParams& p, const int* bt_s, int t) {
+  const int i = t / p.block_size;
+  return p.max_blocks <= kDsBtSmem ? bt_s[i] : p.block_table[i];
+}
+// K and V slices of TB tokens (tb, tb + kDsWarps, ...) of kv head h into registers; the new token (t == pos) and tokens past
+// the split's end are left zero (the new token's k / v come from shared memory when the scores are computed)
+template <int HD, int TB>
+SSDK_DEVINL void ds_load_kv(const DsParams& p, const int* bt_s, const __nv_bfloat16* kbase, const __nv_bfloat16* vbase, int h,
+                            int tb, int t1, int pos, int lane, float (&kv)[TB][HD / 32], float (&vv)[TB][HD / 32]) {
+  constexpr int EPL = HD / 32;
+  static_assert(EPL == 2 || EPL == 4, "head_dim 64 or 128");
+#pragma unroll
+  for (int u = 0; u < TB; ++u) {
+    const int t = tb + u * kDsWarps;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) kv[u][e] = vv[u][e] = 0.f;
+    if (t < t1 && t != pos) {
+      const int blk = ds_page_of(p, bt_s, t);
+      const size_t off = (((size_t)blk * p.block_size + t % p.block_size) * p.KV + h) * HD + lane * EPL;
+      if constexpr (EPL == 2) {
+        const float2 a = ds_bf2(__ldcg(reinterpret_cast<const uint32_t*>(kbase + off)));
+        const float2 b = ds_bf2(__ldcg(reinterpret_cast<const uint32_t*>(vbase + off)));
+        kv[u][0] = a.x; kv[u][1] = a.y; vv[u][0] = b.x; vv[u][1] = b.y;
+      } else {
+        const uint2 a = __ldcg(reinterpret_cast<const uint2*>(kbase + off));
+        const uint2 b = __ldcg(reinterpret_cast<const uint2*>(vbase + off));
+        float2 f = ds_bf2(a.x); kv[u][0] = f.x; kv[u][1] = f.y;
+        f = ds_bf2(a.y); kv[u][EPL - 2] = f.x; kv[u][EPL - 1] = f.y;
+        f = ds_bf2(b.x); vv[u][0] = f.x; vv[u][1] = f.y;
+        f = ds_bf2(b.y); vv[u][EPL - 2] = f.x; vv[u][EPL - 1] = f.y;
+      }
+    }
+  }
+}
 template <int HD, int GMAX>
-SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, int ns, int ctx, float* sm, int* flag) {
+SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, int ns, int ctx, float* sm, int* flag,
+                                   const int* bt_s) {
   constexpr int HALF = HD / 2;
   constexpr int EPL = HD / 32;  // elements per lane in the dot layout (dims lane*EPL ..)
+  constexpr int TB = 4;         // tokens per warp iteration
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = p.H / p.KV;
   const int pos = ctx - 1;
@@ -461,6 +499,15 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
   float* sk = sq + GMAX * HD;          // [HD] new k
   float* sv = sk + HD;                 // [HD] new v
   float* sred = sv + HD;               // [kDsWarps][G][HD + 2] per-warp partials
+
+  // ---- token range of this split; the cached K / V of the first warp iteration are requested NOW: they do not depend on
+  //      phase A, so their L2 / HBM round trip overlaps the one of the q|k|v vector below ----
+  const int per = (ctx + ns - 1) / ns;
+  const int t0 = s * per, t1 = min(ctx, t0 + per);
+  const __nv_bfloat16* kbase = p.k_cache + (size_t)layer * p.cache_layer_stride;
+  const __nv_bfloat16* vbase = p.v_cache + (size_t)layer * p.cache_layer_stride;
+  float kv[TB][EPL], vv[TB][EPL];
+  ds_load_kv<HD, TB>(p, bt_s, kbase, vbase, h, t0 + warp, t1, pos, lane, kv, vv);
 
   // ---- q rows, k, v: one warp per row, rotate-half pairs (i, i + HALF) ----
   const float* cs = p.rope + (size_t)pos * HD;
@@ -520,7 +567,7 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
   ds_sync();
 
   // ---- KV store of the new token (one unit per kv head) ----
-  const int blk_new = p.block_table[pos / p.block_size];
+  const int blk_new = ds_page_of(p, bt_s, pos);
   if (s == 0 && blk_new >= 0) {
     const size_t slot = (size_t)blk_new * p.block_size + pos % p.block_size;
     __nv_bfloat16* kc = p.k_cache + (size_t)layer * p.cache_layer_stride + (slot * p.KV + h) * HD;
@@ -530,10 +577,6 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
       vc[i] = f2bf(sv[i]);
     }
   }
-
-  // ---- token range of this split ----
-  const int per = (ctx + ns - 1) / ns;
-  const int t0 = s * per, t1 = min(ctx, t0 + per);
 
   // dot layout: lane owns dims [lane * EPL, lane * EPL + EPL)
   float qreg[GMAX][EPL];
@@ -549,46 +592,21 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
 #pragma unroll
     for (int e = 0; e < EPL; ++e) acc[g][e] = 0.f;
   }
-  const __nv_bfloat16* kbase = p.k_cache + (size_t)layer * p.cache_layer_stride;
-  const __nv_bfloat16* vbase = p.v_cache + (size_t)layer * p.cache_layer_stride;
   // four tokens per warp iteration: all eight K / V loads are in flight before the first score is computed (one token
   // per iteration exposed a full L2 / HBM round trip per token)
-  constexpr int TB = 4;
   for (int tb = t0 + warp; tb < t1; tb += TB * kDsWarps) {
-    float kv[TB][EPL], vv[TB][EPL];
+    if (tb != t0 + warp) ds_load_kv<HD, TB>(p, bt_s, kbase, vbase, h, tb, t1, pos, lane, kv, vv);
 #pragma unroll
     for (int u = 0; u < TB; ++u) {
       const int t = tb + u * kDsWarps;
-      if (t >= t1) {
+      if (t < t1) {
+        if (t == pos) {
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) kv[u][e] = vv[u][e] = 0.f;
-      } else if (t == pos) {
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-          kv[u][e] = sk[lane * EPL + e];
-          vv[u][e] = sv[lane * EPL + e];
+          for (int e = 0; e < EPL; ++e) {
+            kv[u][e] = sk[lane * EPL + e];
+            vv[u][e] = sv[lane * EPL + e];
+          }
         }
-      } else {
-        const int blk = p.block_table[t / p.block_size];
-        const size_t off = (((size_t)blk * p.block_size + t % p.block_size) * p.KV + h) * HD + lane * EPL;
-        if constexpr (EPL == 2) {
-          const float2 a = ds_bf2(__ldcg(reinterpret_cast<const uint32_t*>(kbase + off)));
-          const float2 b = ds_bf2(__ldcg(reinterpret_cast<const uint32_t*>(vbase + off)));
-          kv[u][0] = a.x; kv[u][1] = a.y; vv[u][0] = b.x; vv[u][1] = b.y;
-        } else {
-          static_assert(EPL == 2 || EPL == 4, "head_dim 64 or 128");
-          const uint2 a = __ldcg(reinterpret_cast<const uint2*>(kbase + off));
-          const uint2 b = __ldcg(reinterpret_cast<const uint2*>(vbase + off));
-          float2 f = ds_bf2(a.x); kv[u][0] = f.x; kv[u][1] = f.y;
-          f = ds_bf2(a.y); kv[u][EPL - 2] = f.x; kv[u][EPL - 1] = f.y;
-          f = ds_bf2(b.x); vv[u][0] = f.x; vv[u][1] = f.y;
-          f = ds_bf2(b.y); vv[u][EPL - 2] = f.x; vv[u][EPL - 1] = f.y;
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < TB; ++u) {
-      if (tb + u * kDsWarps < t1) {
 #pragma unroll
         for (int g = 0; g < GMAX; ++g) {
           if (g < G) {
@@ -696,9 +714,11 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
   SSDK_STATIC_SMEM(ArgMax, ared, 32);
   SSDK_SHARED_VAR(int, tok_s);
   SSDK_SHARED_VAR(int, flag_s);
+  SSDK_STATIC_SMEM(int, bt_s, kDsBtSmem);
   // dynamic shared memory: [ring: n_slots x 32 KB][xs: max(d, ffn, H*HD) floats][attention scratch]
   float* xs = reinterpret_cast<float*>(ds_smem + (size_t)p.n_slots * kDsSlotBytes);
   float* scratch = xs + max(max(p.d, p.ffn), p.H * HD);
+  if (threadIdx.x < kDsBtSmem && (int)threadIdx.x < p.max_blocks) bt_s[threadIdx.x] = p.block_table[threadIdx.x];
   if (threadIdx.x == 0) {
     trace_mark(TR_MISC);
     ds_geometry(p.d, (p.H + 2 * p.KV) * HD, false, &geom[DS_QKV]);
@@ -767,7 +787,7 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
       // ---- B: RoPE + KV store + attention units (+ merge by the last split of each kv head) ----
       const int ns = ds_num_splits(ctx);
       for (int u = blockIdx.x; u < p.KV * ns; u += gridDim.x)
-        ds_attention_unit<HD, GMAX>(p, l, u / ns, u % ns, ns, ctx, scratch, &flag_s);
+        ds_attention_unit<HD, GMAX>(p, l, u / ns, u % ns, ns, ctx, scratch, &flag_s, bt_s);
       ds_mark(f, 3);
       bar.sync();
       ds_mark(f, 4);

@@ -857,7 +857,7 @@ static bool draft_stream_enabled() {
   if (v < 0) v = env_int("SSDK_DRAFT_STREAM", 1) != 0 ? 1 : 0;
   return v == 1;
 }
-constexpr int kMaxDynSmem = 227 * 1024 - 1024;  // opt-in limit per CTA minus the kernels' static shared memory
+constexpr int kMaxDynSmem = 227 * 1024 - 2048;  // opt-in limit per CTA minus the kernel's static shared memory (1.8 KB)
 static size_t ds_fixed_smem(const Model& m) {
   const int G = m.H / m.KV, gmax = G <= 4 ? 4 : 8;
   const size_t xs = (size_t)std::max(std::max(m.d, m.ffn), m.H * m.hd);
