@@ -59,9 +59,11 @@ def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims
     cfg = ModelCfg(hidden=hidden, layers=2, heads=heads, kv_heads=max(1, heads // 2), head_dim=hd, ffn=ffn, vocab=264,
                    max_pos=512, rms_eps=1e-5 if family == "llama" else 1e-6, rope_theta=500000.0, qk_norm=(family != "llama"))
     w = random_weights(cfg, seed=9)
-    nblk = 6
+    # page table: 6 entries (staged in shared memory by the kernel) or, for the K = 4096 case, 40 entries (> kDsBtSmem:
+    # the kernel reads the table from global memory)
+    nblk = 40 if ffn == 4096 else 6
     model = OracleModel(cfg, w, num_blocks=nblk, block_size=bs)
-    bt = [4, 1, 5, 0, 3, 2]
+    bt = [4, 1, 5, 0, 3, 2] + list(range(6, nblk))
     prompt = torch.randint(0, cfg.vocab, (n,))
     slots = torch.tensor([bt[p // bs] * bs + p % bs for p in range(n)], dtype=torch.int32)
     btt = torch.tensor([bt], dtype=torch.int32)
