@@ -27,6 +27,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -120,17 +121,16 @@ def run_reference_gpu_subprocess(args, timeout_s: int = 480):
     if args.lm_scale:
         cmd += ["--lm-scale", str(args.lm_scale)]
     t0 = time.time()
+    res = None
     try:
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
         with open(out_path) as f:
             d = json.loads(f.read())
-    except Exception as exc:  # noqa: BLE001
-        tail = ""
-        try:
-            tail = (res.stdout + res.stderr)[-300:]
-        except Exception:
-            pass
+    except Exception as exc:  # noqa: BLE001  (timeout, crash before the result file was written, malformed result)
+        tail = (res.stdout + res.stderr)[-300:] if res is not None else ""
         d = {"impl": "reference-gpu", "unavailable": f"{type(exc).__name__}: {exc} {tail}"[:500]}
+    finally:
+        shutil.rmtree(os.path.dirname(out_path), ignore_errors=True)
     d["wall_s"] = round(time.time() - t0, 1)
     return d
 
