@@ -214,3 +214,30 @@ def test_prefill_call_planner_packs_equal_prompts_and_never_loses_tokens():
     r = Rec()
     r.prefill_many(0, [list(range(128))] * 16, [[i] for i in range(16)], [0] * 16)
     assert len(r.calls) == 8
+
+
+def test_kv_budget_draft_cache_is_sized_from_what_the_target_left(monkeypatch):
+    """loader.kv_blocks_for (allocate_kv_cache, engine/model_runner.py:446-476; draft_runner.py:27): both caches are carved
+    out of ONE free-memory snapshot, so the draft's share is taken from what remains after the target's; the result never
+    exceeds what max_num_seqs sequences of max_model_len can use and never drops below one block."""
+    import torch
+    from ssd_b200 import loader
+    spec_t = types.SimpleNamespace(layers=80, kv_heads=8, head_dim=128)
+    spec_d = types.SimpleNamespace(layers=16, kv_heads=8, head_dim=64)
+    cfg = types.SimpleNamespace(kvcache_block_size=256, gpu_memory_utilization=0.9, max_num_seqs=64, max_blocks=32)
+    free = 30 << 30
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a: (free, 180 << 30))
+    bt = loader.kv_block_bytes(cfg, spec_t, 1)
+    assert bt == 2 * 80 * 256 * 8 * 128 * 2 and loader.kv_block_bytes(cfg, spec_t, 4) == bt // 4
+    nbt = loader.kv_blocks_for(cfg, spec_t, 1, 0.8)
+    assert nbt == int(free * 0.9 * 0.8) // bt
+    nbd = loader.kv_blocks_for(cfg, spec_d, 1, 0.75, reserved=nbt * bt)
+    bd = loader.kv_block_bytes(cfg, spec_d, 1)
+    assert nbd == int((free - nbt * bt) * 0.9 * 0.75) // bd
+    assert nbt * bt + nbd * bd <= free, "the two caches together must fit the free memory of the snapshot"
+    # without the reservation the draft would have been promised memory the target already holds
+    assert loader.kv_blocks_for(cfg, spec_d, 1, 0.75) * bd + nbt * bt > free
+    # cap: never more blocks than the sequences can use; floor: one block
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a: (170 << 30, 180 << 30))
+    assert loader.kv_blocks_for(cfg, spec_d, 1, 0.75) == 64 * 32 * 2 + 2
+    assert loader.kv_blocks_for(cfg, spec_t, 1, 0.8, reserved=200 << 30) == 1
