@@ -390,7 +390,13 @@ SSDK_DEVINL unsigned atom_add_acq_rel_gpu(unsigned* p, unsigned v) { return __at
 SSDK_DEVINL void red_add_release_gpu_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELEASE); }
 SSDK_DEVINL unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
   std::this_thread::yield();
+#if defined(__SANITIZE_THREAD__)
+  // ThreadSanitizer does not model atomic_thread_fence: the "relaxed poll + one acquire fence" of the device-wide barrier
+  // would show up as races on everything the barrier orders.  Under TSan the poll itself acquires.
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
   return __atomic_load_n(p, __ATOMIC_RELAXED);
+#endif
 }
 SSDK_DEVINL void fence_acq_rel_gpu() { std::atomic_thread_fence(std::memory_order_acq_rel); }
 SSDK_DEVINL void st_relaxed_gpu_u32(unsigned* p, unsigned v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
