@@ -44,7 +44,9 @@ constexpr int kDsConsumers = 256;                 // threads 0..255: 8 consumer 
 constexpr int kDsWarps = kDsConsumers / 32;
 constexpr int kDsThreads = kDsConsumers + 32;     // + the producer warp
 constexpr int kDsMaxLayers = 32;
-constexpr int kDsSplits = 8;          // KV splits per kv head in phase B
+constexpr int kDsSplits = 16;         // most KV splits per kv head in phase B (long contexts)
+constexpr int kDsShortSplits = 8;     // splits up to kDsLongCtx tokens
+constexpr int kDsLongCtx = 1024;
 constexpr int kDsSlotBytes = 32768;   // one ring slot
 constexpr int kDsMaxSlots = 6;
 constexpr int kDsMaxSteps = 8;        // 256-column steps per K segment (segment <= 2048 columns)
@@ -446,11 +448,15 @@ SSDK_DEVINL void ds_load_vec(const __nv_bfloat16* v, int n, float* xs) {
 // q|k|v vector, stores k / v into the page slot (split 0 only), runs the online-softmax over its token range (the new
 // token comes from shared memory, never from the cache) and writes (o, m, l) per query head.
 // ---------------------------------------------------------------------------------------------
-// KV splits per kv head: all kDsSplits as soon as every split has a few tokens (64 units keep 64 SMs busy for one or two
+// KV splits per kv head: kDsShortSplits as soon as every split has a few tokens (64 units keep 64 SMs busy for one or two
 // 4-token iterations per warp); a single split only for the first tokens of a sequence.  (One split per 256 tokens looked
 // attractive — no partials, ticket or merge below 256 — but the token loop is a chain of dependent L2 round trips per
 // iteration: measured 8B + 1B 10.29 vs 8.34 ms/step.)
-SSDK_DEVINL int ds_num_splits(int ctx) { return min(kDsSplits, max(1, (ctx + 7) >> 3)); }
+// Beyond kDsLongCtx tokens the phase is bound by the number of dependent load rounds per split (warps x tokens in flight):
+// 16 splits per kv head (128 units for 8 kv heads) and 8 tokens per warp iteration quarter the rounds.
+SSDK_DEVINL int ds_num_splits(int ctx) {
+  return ctx > kDsLongCtx ? kDsSplits : min(kDsShortSplits, max(1, (ctx + 7) >> 3));
+}
 // page of token t: from the shared-memory copy of the (launch-constant) page table when it fits, else from global memory
 SSDK_DEVINL int ds_page_of(const DsParams& p, const int* bt_s, int t) {
   const int i = t / p.block_size;
@@ -486,12 +492,11 @@ SSDK_DEVINL void ds_load_kv(const DsParams& p, const int* bt_s, const __nv_bfloa
     }
   }
 }
-template <int HD, int GMAX>
+template <int HD, int GMAX, int TB>  // TB = tokens per warp iteration
 SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, int ns, int ctx, float* sm, int* flag,
                                    const int* bt_s) {
   constexpr int HALF = HD / 2;
   constexpr int EPL = HD / 32;  // elements per lane in the dot layout (dims lane*EPL ..)
-  constexpr int TB = 4;         // tokens per warp iteration
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = p.H / p.KV;
   const int pos = ctx - 1;
@@ -592,7 +597,7 @@ SSDK_DEVINL void ds_attention_unit(const DsParams& p, int layer, int h, int s, i
 #pragma unroll
     for (int e = 0; e < EPL; ++e) acc[g][e] = 0.f;
   }
-  // four tokens per warp iteration: all eight K / V loads are in flight before the first score is computed (one token
+  // TB tokens per warp iteration: all 2 TB K / V loads are in flight before the first score is computed (one token
   // per iteration exposed a full L2 / HBM round trip per token)
   for (int tb = t0 + warp; tb < t1; tb += TB * kDsWarps) {
     if (tb != t0 + warp) ds_load_kv<HD, TB>(p, bt_s, kbase, vbase, h, tb, t1, pos, lane, kv, vv);
@@ -786,8 +791,10 @@ __global__ void __launch_bounds__(kDsThreads, 1) draft_stream_kernel(const __gri
 #endif
       // ---- B: RoPE + KV store + attention units (+ merge by the last split of each kv head) ----
       const int ns = ds_num_splits(ctx);
-      for (int u = blockIdx.x; u < p.KV * ns; u += gridDim.x)
-        ds_attention_unit<HD, GMAX>(p, l, u / ns, u % ns, ns, ctx, scratch, &flag_s, bt_s);
+      for (int u = blockIdx.x; u < p.KV * ns; u += gridDim.x) {
+        if (ns == kDsSplits) ds_attention_unit<HD, GMAX, 8>(p, l, u / ns, u % ns, ns, ctx, scratch, &flag_s, bt_s);
+        else ds_attention_unit<HD, GMAX, 4>(p, l, u / ns, u % ns, ns, ctx, scratch, &flag_s, bt_s);
+      }
       ds_mark(f, 3);
       bar.sync();
       ds_mark(f, 4);

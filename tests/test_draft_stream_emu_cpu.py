@@ -48,6 +48,8 @@ def _u16(t):
                                                   # two KV splits per head, partials + ticket + merge by the last split
     ("llama", 3, (256, 4096), 0.0, 2, 21, 16),    # down-proj K = 4096: 4 rows x 2 segments per job
     ("llama", 2, (256, 5120), 0.7, 2, 21, 16),    # down-proj K = 5120: 2 rows x 4 segments per job
+    ("llama", 3, (256, 512), 0.0, 2, 1100, 64),   # context > 1024: 16 KV splits per head, 8 tokens per warp iteration,
+                                                  # several attention units per CTA
 ])
 def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims, temp, n_fwd, n, bs):
     from oracle import verify as V
@@ -57,11 +59,11 @@ def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims
     hidden, ffn = dims
     heads = hidden // hd if family == "llama" else max(2, hidden // hd)
     cfg = ModelCfg(hidden=hidden, layers=2, heads=heads, kv_heads=max(1, heads // 2), head_dim=hd, ffn=ffn, vocab=264,
-                   max_pos=512, rms_eps=1e-5 if family == "llama" else 1e-6, rope_theta=500000.0, qk_norm=(family != "llama"))
+                   max_pos=2048 if n > 1000 else 512, rms_eps=1e-5 if family == "llama" else 1e-6, rope_theta=500000.0, qk_norm=(family != "llama"))
     w = random_weights(cfg, seed=9)
     # page table: 6 entries (staged in shared memory by the kernel) or, for the K = 4096 case, 40 entries (> kDsBtSmem:
     # the kernel reads the table from global memory)
-    nblk = 40 if ffn == 4096 else 6
+    nblk = 40 if ffn == 4096 else (20 if n > 1000 else 6)
     model = OracleModel(cfg, w, num_blocks=nblk, block_size=bs)
     bt = [4, 1, 5, 0, 3, 2] + list(range(6, nblk))
     prompt = torch.randint(0, cfg.vocab, (n,))

@@ -1,7 +1,10 @@
 """Validate the streaming draft kernel (csrc/draft_stream.cuh, one persistent launch per step for the K+1 draft forwards
 and their samplings) against the kernel-per-op path (SSDK_DRAFT_STREAM=0).
 
-    python tools/check_draft_stream.py [--temp 0.7]      # runs the modes in subprocesses and compares
+    python tools/check_draft_stream.py [--temp 0.7] [--prompt-len 3000] [--parallel]
+                                                         # runs the modes in subprocesses and compares; --prompt-len > 1024
+                                                         # exercises the long-context attention (16 KV splits); --parallel
+                                                         # runs the modes at the same time (correctness only, timings mixed)
 
 Workload: a 2-layer target at Llama-3.1-8B dimensions + the full 16-layer Llama-3.2-1B draft (real draft shapes, synthetic
 bigram-agreement weights), k=6, b=1.  SD output equals AR output whatever the draft does, so the check is on the DRAFT
@@ -18,6 +21,7 @@ sys.path.insert(0, ROOT)
 
 
 TEMP = float(sys.argv[sys.argv.index("--temp") + 1]) if "--temp" in sys.argv else 0.0
+PROMPT = int(sys.argv[sys.argv.index("--prompt-len") + 1]) if "--prompt-len" in sys.argv else 200
 
 
 def worker(out_path):
@@ -32,10 +36,10 @@ def worker(out_path):
     root = tempfile.mkdtemp()
     llm = LLM(synth.make_model_dir(root, "llama-3.1-8b", "target", layers=2), speculate=True,
               draft=synth.make_model_dir(root, "llama-3.2-1b", "draft"), speculate_k=6, num_gpus=1, max_num_seqs=1,
-              max_model_len=2048, jit_speculate=True)
+              max_model_len=max(2048, (PROMPT + 24 * 7 + 263) // 256 * 256), jit_speculate=True)
     r = llm.runner
     random.seed(0)
-    prompt = [random.randint(0, 10000) for _ in range(200)]
+    prompt = [random.randint(0, 10000) for _ in range(PROMPT)]
     bt = list(range(r.max_blocks))
     rec = r.prefill(L.TARGET, prompt, bt)
     r.prefill(L.DRAFT, prompt, bt, want_sample=False)
@@ -68,16 +72,20 @@ def main():
     res = {}
     tmp = tempfile.mkdtemp()
     modes = (("regular", {"SSDK_DRAFT_STREAM": "0"}), ("stream", {"SSDK_DRAFT_STREAM": "1"}))
-    extra = ["--temp", str(TEMP)] if TEMP else []
+    extra = (["--temp", str(TEMP)] if TEMP else []) + ["--prompt-len", str(PROMPT)]
+    procs = []
     for mode, env in modes:
         out = os.path.join(tmp, mode + ".npz")
-        rc = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", out] + extra,
-                            env={**os.environ, **env}, timeout=600).returncode
-        if rc != 0:
-            sys.exit(f"{mode} run failed (rc={rc})")
+        pr = subprocess.Popen([sys.executable, os.path.abspath(__file__), "--worker", out] + extra, env={**os.environ, **env})
+        procs.append((mode, out, pr))
+        if "--parallel" not in sys.argv:
+            pr.wait(timeout=600)
+    for mode, out, pr in procs:
+        if pr.wait(timeout=600) != 0:
+            sys.exit(f"{mode} run failed (rc={pr.returncode})")
         res[mode] = np.load(out)
     a = res["regular"]
-    report = {"temp": TEMP, "mean_accept_len": float(a["nacc"].mean() + 1), "ms_per_step": {}, "same_tokens": {},
+    report = {"temp": TEMP, "prompt_len": PROMPT, "mean_accept_len": float(a["nacc"].mean() + 1), "ms_per_step": {}, "same_tokens": {},
               "draft_logits_max_abs_diff": {}, "draft_logits_max_abs": float(np.abs(a["lq"]).max())}
     bad = False
     for mode, _ in modes:
