@@ -22,7 +22,7 @@ workload, _, nl = workload.partition(":")
 shapes = {"8b": ("llama-3.1-8b", "llama-3.2-1b"), "70b": ("llama-3.1-70b", "llama-3.2-1b")}[workload]
 root = tempfile.mkdtemp()
 llm = LLM(synth.make_model_dir(root, shapes[0], "target", layers=int(nl) if nl else None), speculate=True, draft=synth.make_model_dir(root, shapes[1], "draft"),
-          speculate_k=6, num_gpus=world, max_num_seqs=1, max_model_len=4096, jit_speculate=True, use_pdl=("--no-pdl" not in sys.argv))
+          speculate_k=6, num_gpus=world, max_num_seqs=1, max_model_len=int(sys.argv[sys.argv.index('--max-len') + 1]) if '--max-len' in sys.argv else 4096, jit_speculate=True, use_pdl=("--no-pdl" not in sys.argv))
 r = llm.runner
 random.seed(0)
 prompt = [random.randint(0, 10000) for _ in range(128)]
