@@ -894,9 +894,7 @@ static int launch_draft_stream(Launcher& L, const DsParams& p, size_t smem) {
   attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: the phases meet at device-wide barriers
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  // SSDK_DRAFT_COOP=0 (experiment): plain launch.  One CTA per SM on an otherwise idle stream is co-resident in practice (the
-  // kernel before it has drained: this launch carries no PDL attribute); the barriers trap instead of hanging if it is not.
-  cfg.numAttrs = env_int("SSDK_DRAFT_COOP", 1) != 0 ? 1 : 0;
+  cfg.numAttrs = 1;  // (a plain launch measured the same step time: 5.70 vs 5.66 ms — the attribute costs nothing between steps)
   cudaError_t err = cudaLaunchKernelEx(&cfg, draft_stream_kernel<HD, GMAX>, p);
   if (err != cudaSuccess) return fail("draft stream launch failed: %s", cudaGetErrorString(err));
   L.barrier_op();  // not a PDL primary: the next kernel starts after this grid has drained
