@@ -48,7 +48,8 @@ def _u16(t):
                                                   # two KV splits per head, partials + ticket + merge by the last split
     ("llama", 3, (256, 4096), 0.0, 2, 21, 16),    # down-proj K = 4096: 4 rows x 2 segments per job
     ("llama", 2, (256, 5120), 0.7, 2, 21, 16),    # down-proj K = 5120: 2 rows x 4 segments per job
-    ("llama", 3, (256, 512), 0.0, 2, 1100, 64),   # context > 1024: 16 KV splits per head, 8 tokens per warp iteration,
+    ("llama", 3, (256, 512), 0.0, 4, 1022, 64),   # context 1023 .. 1026 inside ONE launch: the forwards switch from 8 KV splits
+                                                  # (4 tokens per warp iteration) to 16 splits (8 tokens) at 1025 tokens;
                                                   # several attention units per CTA
 ])
 def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims, temp, n_fwd, n, bs):
