@@ -307,7 +307,8 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "parity_check": parity,
         "allreduce": ("none" if world == 1 else ("symm" if getattr(runner, "symm", False) else "nccl")),
-        "draft_path": "kernel-per-op" if os.environ.get("SSDK_DRAFT_STREAM", "1") == "0" else "draft_stream_kernel (one launch per step)",
+        "draft_path": "kernel-per-op" if os.environ.get("SSDK_DRAFT_STREAM", "1") == "0"
+        else "draft_stream_kernel (one launch per step; kernel-per-op graph beyond 1024 tokens of context)",
         "reference_gpu": ref_gpu,
     }
     if args.lm_scale:

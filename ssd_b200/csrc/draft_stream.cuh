@@ -46,7 +46,7 @@ constexpr int kDsThreads = kDsConsumers + 32;     // + the producer warp
 constexpr int kDsMaxLayers = 32;
 constexpr int kDsSplits = 16;         // most KV splits per kv head in phase B (long contexts)
 constexpr int kDsShortSplits = 8;     // splits up to kDsLongCtx tokens
-constexpr int kDsLongCtx = 1024;
+constexpr int kDsLongCtx = 256;       // = kDsShortSplits x 8 warps x 4 tokens: the most ONE load round of the short layout covers
 constexpr int kDsSlotBytes = 32768;   // one ring slot
 constexpr int kDsMaxSlots = 6;
 constexpr int kDsMaxSteps = 8;        // 256-column steps per K segment (segment <= 2048 columns)
@@ -452,8 +452,10 @@ SSDK_DEVINL void ds_load_vec(const __nv_bfloat16* v, int n, float* xs) {
 // 4-token iterations per warp); a single split only for the first tokens of a sequence.  (One split per 256 tokens looked
 // attractive — no partials, ticket or merge below 256 — but the token loop is a chain of dependent L2 round trips per
 // iteration: measured 8B + 1B 10.29 vs 8.34 ms/step.)
-// Beyond kDsLongCtx tokens the phase is bound by the number of dependent load rounds per split (warps x tokens in flight):
-// 16 splits per kv head (128 units for 8 kv heads) and 8 tokens per warp iteration quarter the rounds.
+// The phase is bound by the number of dependent load ROUNDS per split (a round = warps x tokens in flight; each further
+// round measured 5 - 8 us per layer): up to 256 tokens 8 splits x 8 warps x 4 tokens cover the context in one round; beyond,
+// 16 splits per kv head (128 units for 8 kv heads) and 8 tokens per warp iteration keep it at one round up to 1024 tokens
+// (the engine takes the kernel-per-op draft for longer contexts, use_draft_stream in engine.cu).
 SSDK_DEVINL int ds_num_splits(int ctx) {
   return ctx > kDsLongCtx ? kDsSplits : min(kDsShortSplits, max(1, (ctx + 7) >> 3));
 }

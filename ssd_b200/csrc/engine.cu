@@ -318,9 +318,10 @@ struct ssdk_engine {
   size_t off_ctx, off_rec, off_tt, off_tq, off_seed, off_btt, off_btd;
   size_t off_out_nacc, off_out_rec;
   // graphs
-  std::map<int, cudaGraphExec_t> spec_graphs;  // keyed by batch
+  std::map<int, cudaGraphExec_t> spec_graphs;  // keyed by batch * 2 + (draft path: 1 = streaming kernel)
   std::map<int, int64_t> spec_graph_launches;
   std::map<int, cudaGraphExec_t> spec_graphs_resident;
+  int resident_ctx_bound = 0;  // upper bound of the resident loop's context length (staged value + (K+1) per step)
   int max_ctx_hint = 0;
   cudaStream_t cap_stream = nullptr;
   // one-shot all-reduce over NVLink symmetric memory (optional; NCCL is used when not bound)
@@ -878,6 +879,20 @@ static bool draft_stream_supported(const Model& m, int B) {
          ds_geometry(m.d, m.ffn, true, &g) && ds_geometry(m.ffn, m.d, false, &g) && ds_geometry(m.d, m.cfg.vocab, false, &g) &&
          ds_ring_slots(m) >= 3;
 }
+// Which draft path a step takes.  The streaming kernel wins while the attention phase of a KV split is ONE round of loads
+// (16 splits x 8 warps x 8 tokens = 1024 tokens); every further round costs more than the kernel-per-op draft's tensor-core
+// attention (measured at ~3k tokens: +2.4 ms per step, profiles/r02_draft_stream.md), so longer contexts take the
+// kernel-per-op graph.  Both graphs compute the same step; ctx_bound = the longest context of the batch before the step.
+static int draft_stream_max_ctx() {
+  static int v = -1;
+  if (v < 0) v = std::max(0, env_int("SSDK_DRAFT_STREAM_MAX_CTX", 1024));
+  return v;
+}
+static bool use_draft_stream(ssdk_engine* e, int B, int ctx_bound) {
+  const Model& drf = e->model[SSDK_DRAFT];
+  return drf.present && draft_stream_enabled() && draft_stream_supported(drf, B) &&
+         ctx_bound + e->rt.spec_k + 1 <= draft_stream_max_ctx();
+}
 template <int HD, int GMAX>
 static int launch_draft_stream(Launcher& L, const DsParams& p, size_t smem) {
   static bool attr_set = false;
@@ -945,7 +960,7 @@ static int enqueue_draft_stream(ssdk_engine* e, Launcher& L, int64_t* tok_buf, i
   return launch_draft_stream<128, 8>(L, p, smem);
 }
 
-static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, bool advance) {
+static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, bool advance, bool stream_draft) {
   Workspace& w = e->ws;
   const int K = e->rt.spec_k;
   Model& tgt = e->model[SSDK_TARGET];
@@ -967,7 +982,6 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
   if (tp > 1 && !e->comm) return fail("tensor parallel spec step without a NCCL communicator");
   if (tp_rank == 0 && !drf.present) return fail("rank 0 needs the draft model");
   if (drf.present) CKI(L.go(init_tokens_kernel, dim3(1), dim3(64), 0, (const int64_t*)rec_in, w.tok_buf, B, K + 1));
-  const bool stream_draft = drf.present && draft_stream_enabled() && draft_stream_supported(drf, B);
   if (stream_draft)
     CKI(enqueue_draft_stream(e, L, w.tok_buf, K + 1, true, ctx, btd, tq, seed_step, w.logits_q, (int64_t)V));
   for (int k = 0; k <= K && drf.present && !stream_draft; ++k) {
@@ -1025,13 +1039,14 @@ static int enqueue_spec_step(ssdk_engine* e, Launcher& L, int B, bool host_io, b
   return 0;
 }
 
-static int get_spec_graph(ssdk_engine* e, int B, bool host_io, cudaStream_t st, cudaGraphExec_t* out, int64_t* nlaunch) {
+static int get_spec_graph(ssdk_engine* e, int B, bool host_io, bool stream_draft, cudaStream_t st, cudaGraphExec_t* out,
+                          int64_t* nlaunch) {
   auto& cache = host_io ? e->spec_graphs : e->spec_graphs_resident;
-  const int key = B;
+  const int key = B * 2 + (stream_draft ? 1 : 0);
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
-    *nlaunch = e->spec_graph_launches[B];
+    *nlaunch = e->spec_graph_launches[key];
     return 0;
   }
   (void)st;
@@ -1041,7 +1056,7 @@ static int get_spec_graph(ssdk_engine* e, int B, bool host_io, cudaStream_t st, 
   L.pdl = e->rt.use_pdl != 0;
   cudaGraph_t graph = nullptr;
   CK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
-  const int rc = enqueue_spec_step(e, L, B, host_io, !host_io);
+  const int rc = enqueue_spec_step(e, L, B, host_io, !host_io, stream_draft);
   cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
   if (rc != 0) {
     if (graph) cudaGraphDestroy(graph);
@@ -1053,7 +1068,7 @@ static int get_spec_graph(ssdk_engine* e, int B, bool host_io, cudaStream_t st, 
   cudaGraphDestroy(graph);
   if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
   cache[key] = exec;
-  e->spec_graph_launches[B] = L.count;
+  e->spec_graph_launches[key] = L.count;
   *out = exec;
   *nlaunch = L.count;
   return 0;
@@ -1321,17 +1336,18 @@ int ssdk_spec_step(ssdk_handle h, int batch, const int32_t* ctx_len, const int64
   if (h->rt.spec_k < 1) return fail("spec_step: engine built without speculation");
   cudaStream_t st = (cudaStream_t)stream;
   CKI(fill_step(h, batch, ctx_len, recovery, block_tables_target, block_tables_draft, temp_t, temp_q, seed, step_id));
+  const bool stream_draft = use_draft_stream(h, batch, *std::max_element(ctx_len, ctx_len + batch));
   if (h->rt.use_graph) {
     cudaGraphExec_t g;
     int64_t n;
-    CKI(get_spec_graph(h, batch, true, st, &g, &n));
+    CKI(get_spec_graph(h, batch, true, stream_draft, st, &g, &n));
     CK(cudaGraphLaunch(g, st));
     h->launches += n;
   } else {
     Launcher L;
     L.st = st;
     L.pdl = h->rt.use_pdl != 0;
-    CKI(enqueue_spec_step(h, L, batch, true, false));
+    CKI(enqueue_spec_step(h, L, batch, true, false, stream_draft));
     h->launches += L.count;
   }
   CK(cudaStreamSynchronize(st));
@@ -1345,6 +1361,7 @@ int ssdk_spec_step_stage(ssdk_handle h, int batch, const int32_t* ctx_len, const
   if (!h || !h->finalized) return fail("spec_step_stage: engine not finalized");
   cudaStream_t st = (cudaStream_t)stream;
   CKI(fill_step(h, batch, ctx_len, recovery, block_tables_target, block_tables_draft, temp_t, temp_q, seed, step_id));
+  h->resident_ctx_bound = *std::max_element(ctx_len, ctx_len + batch);
   CK(cudaMemcpyAsync(h->ws.step_dev, h->pin_in, h->step_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(h->ws.log_len, 0, (size_t)h->rt.max_batch * 4, st));
   CK(cudaStreamSynchronize(st));
@@ -1355,17 +1372,20 @@ int ssdk_spec_step_resident(ssdk_handle h, int batch, void* stream) {
   if (!h || !h->finalized) return fail("spec_step_resident: engine not finalized");
   if (h->rt.spec_k < 1) return fail("spec_step: engine built without speculation");
   cudaStream_t st = (cudaStream_t)stream;
+  // the context lives on the device here; the host keeps an upper bound (every step appends at most K+1 tokens)
+  const bool stream_draft = use_draft_stream(h, batch, h->resident_ctx_bound);
+  h->resident_ctx_bound += h->rt.spec_k + 1;
   if (h->rt.use_graph) {
     cudaGraphExec_t g;
     int64_t n;
-    CKI(get_spec_graph(h, batch, false, st, &g, &n));
+    CKI(get_spec_graph(h, batch, false, stream_draft, st, &g, &n));
     CK(cudaGraphLaunch(g, st));
     h->launches += n;
   } else {
     Launcher L;
     L.st = st;
     L.pdl = h->rt.use_pdl != 0;
-    CKI(enqueue_spec_step(h, L, batch, false, true));
+    CKI(enqueue_spec_step(h, L, batch, false, true, stream_draft));
     h->launches += L.count;
   }
   return 0;

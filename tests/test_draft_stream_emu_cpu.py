@@ -45,12 +45,13 @@ def _u16(t):
 @pytest.mark.parametrize("family,grid,dims,temp,n_fwd,n,bs", [
     ("llama", 3, (256, 512), 0.0, 3, 21, 16),     # K = 256 / 512: 8 rows per job, one slot (gate|up: 8 pairs, two slots)
     ("qwen", 2, (256, 512), 0.8, 3, 270, 64),     # q/k norm, head_dim 128, Philox sampling in the kernel; context > 256:
-                                                  # two KV splits per head, partials + ticket + merge by the last split
+                                                  # 16 KV splits per head (head_dim 128), partials + ticket + merge by the last split
     ("llama", 3, (256, 4096), 0.0, 2, 21, 16),    # down-proj K = 4096: 4 rows x 2 segments per job
     ("llama", 2, (256, 5120), 0.7, 2, 21, 16),    # down-proj K = 5120: 2 rows x 4 segments per job
-    ("llama", 3, (256, 512), 0.0, 4, 1022, 64),   # context 1023 .. 1026 inside ONE launch: the forwards switch from 8 KV splits
-                                                  # (4 tokens per warp iteration) to 16 splits (8 tokens) at 1025 tokens;
+    ("llama", 3, (256, 512), 0.0, 2, 1100, 64),   # 16 KV splits per head, 8 tokens per warp iteration, two load rounds per split,
                                                   # several attention units per CTA
+    ("llama", 2, (256, 512), 0.0, 4, 254, 16),    # context 255 .. 258 inside ONE launch: the forwards switch from 8 KV splits
+                                                  # (4 tokens per warp iteration) to 16 splits (8 tokens) at 257 tokens
 ])
 def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims, temp, n_fwd, n, bs):
     from oracle import verify as V
@@ -64,7 +65,7 @@ def test_draft_stream_kernel_source_on_host_threads(tmp_path, family, grid, dims
     w = random_weights(cfg, seed=9)
     # page table: 6 entries (staged in shared memory by the kernel) or, for the K = 4096 case, 40 entries (> kDsBtSmem:
     # the kernel reads the table from global memory)
-    nblk = 40 if ffn == 4096 else (20 if n > 1000 else 6)
+    nblk = 40 if ffn == 4096 else max(6, (n + n_fwd) // bs + 2)
     model = OracleModel(cfg, w, num_blocks=nblk, block_size=bs)
     bt = [4, 1, 5, 0, 3, 2] + list(range(6, nblk))
     prompt = torch.randint(0, cfg.vocab, (n,))

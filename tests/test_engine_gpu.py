@@ -354,3 +354,51 @@ def test_packed_prefill_of_ragged_prompts_matches_oracle():
         rec = nrec.tolist()
         s.advance(nacc.tolist(), rec)
     r.close()
+
+
+def test_spec_steps_across_the_draft_path_switch_match_oracle():
+    """The step graph takes the streaming draft kernel while the context fits one load round of its attention phase
+    (<= 1024 tokens incl. the K+1 new ones) and the kernel-per-op draft beyond (use_draft_stream, csrc/engine.cu).  A
+    sequence that starts at 1012 tokens crosses the limit within ten steps: every step — whichever graph ran it, and the
+    KV the other one left behind — must agree with the oracle (teacher-forced, near-tie protocol); the contexts in between
+    also run the 16-split layout of the streaming kernel's attention (> 256 tokens)."""
+    from oracle.model import ModelCfg, OracleModel, random_weights
+    from oracle.spec import SpecSession, check_greedy_step, contiguous_block_tables
+    from ssd_b200 import lib as L
+    from ssd_b200.runner import PairRunner
+    dev = torch.device("cuda:0")
+    K, bs, mb = 4, 64, 18
+    tc = ModelCfg(hidden=256, layers=2, heads=4, kv_heads=2, head_dim=64, ffn=512, vocab=1024, max_pos=bs * mb)
+    dc = ModelCfg(**{**tc.__dict__, "layers": 1})
+    wt = random_weights(tc, 29)
+    wd = {"embed": wt["embed"], "lm_head": wt["lm_head"], "final_norm": wt["final_norm"], "layers": [wt["layers"][0]]}
+    r = PairRunner(_spec(tc), _spec(dc), spec_k=K, max_batch=1, block_size=bs, max_model_len=bs * mb, use_graph=True)
+    r.bind_weights(L.TARGET, _to_dev(wt, dev))
+    r.bind_weights(L.DRAFT, _to_dev(wd, dev))
+    r.finalize()
+    g = torch.Generator().manual_seed(5)
+    prompt = torch.randint(0, tc.vocab, (1012,), generator=g).tolist()
+    bt = contiguous_block_tables(1, mb)
+    s = SpecSession(OracleModel(tc, wt, mb, bs), OracleModel(dc, wd, mb, bs), K, mb)
+    rec_o = s.prefill([prompt], [0.0], bt, bt.clone())
+    r.prefill(L.TARGET, prompt, bt[0].tolist())
+    r.prefill(L.DRAFT, prompt, bt[0].tolist(), want_sample=False)
+    ctx, rec = len(prompt), rec_o[0]
+    launches = []
+    for step in range(10):
+        n0 = r.launch_count()
+        toks, nacc, nrec = r.spec_step([ctx], [rec], [bt[0].tolist()], [bt[0].tolist()], [0.0], [0.0])
+        launches.append(r.launch_count() - n0)
+        spec = torch.from_numpy(toks)
+        lp_o, lq_o = s.spec_step_forced(spec)
+        torch.testing.assert_close(r.logits_p(1).cpu().float(), lp_o.float(), atol=0.08, rtol=0.03)
+        torch.testing.assert_close(r.logits_q(1).cpu().float(), lq_o.float(), atol=0.08, rtol=0.03)
+        hard, _ = check_greedy_step(spec, nacc.tolist(), nrec.tolist(), lp_o, lq_o, EPS)
+        assert not hard, f"step {step} (ctx {ctx}): {hard}"
+        ctx += int(nacc[0]) + 1
+        rec = int(nrec[0])
+        s.advance(nacc.tolist(), [rec])
+    assert ctx > 1024 - K - 1, "the sequence never reached the switch"
+    if os.environ.get("SSDK_DRAFT_STREAM", "1") != "0":
+        assert launches[0] < launches[-1], f"one launch for the draft phase below the limit, a kernel per op above: {launches}"
+    r.close()
